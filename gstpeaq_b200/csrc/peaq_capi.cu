@@ -1,0 +1,762 @@
+// C ABI (include/peaq_b200.h) on top of the CUDA kernels: engine (batch path),
+// session (streaming path mirroring one `peaq` element instance), synthetic
+// input generator and small device-memory helpers for FFI hosts.
+#include "../../include/peaq_b200.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "peaq_engine.h"
+#include "peaq_synth.h"
+
+namespace peaq {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define PEAQ_CUDA(expr)                                                                 \
+  do {                                                                                  \
+    cudaError_t err__ = (expr);                                                         \
+    if (err__ != cudaSuccess)                                                           \
+      return fail(PEAQ_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+static_assert(sizeof(PairResult) == sizeof(peaq_b200_result), "result layout mismatch");
+
+// ---------------------------------------------------------------------------
+// kernels that live here: state initialisation and the synthetic generator
+
+// Fresh recurrent state: everything zero (g_new0 in the reference's
+// constructors), accumulators in STATUS_INIT, the windowed-average history
+// primed with NaN (movaccum.c:293), loudness not yet reached (gstpeaq.c:359).
+__global__ void init_state_kernel(double* state, StateLayout S, int n_pairs) {
+  const size_t total = (size_t)n_pairs * S.stride;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int pair = (int)(i / S.stride);
+    const int o = (int)(i - (size_t)pair * S.stride);
+    double v = 0.;
+    if (o >= S.off_acc && o < S.off_scalar) {
+      const int a = (o - S.off_acc) % (kNumAcc * kAccFields);
+      const int slot = a / kAccFields, field = a % kAccFields;
+      if (slot == 3 /* WinModDiff */ && field >= 2 && field <= 4) v = nan("");
+    }
+    if (o == S.off_ints + 1) {
+      // int32 slots 2,3: loudness_reached_frame = G_MAXUINT (gstpeaq.c:359), spare
+      int* ints = reinterpret_cast<int*>(state + i);
+      ints[0] = (int)UINT_MAX;
+      ints[1] = 0;
+    } else {
+      state[i] = v;   // all-zero bits: STATUS_INIT, counters 0
+    }
+  }
+}
+
+__global__ void synth_pairs_kernel(float* __restrict__ ref, float* __restrict__ test,
+                                   size_t pair_stride, unsigned long long first_pair,
+                                   unsigned long long n_samples, int channels) {
+  __shared__ int16_t table[PEAQ_SYNTH_TABLE_SIZE];
+  __shared__ PeaqSynthPair sp;
+  for (int i = threadIdx.x; i < PEAQ_SYNTH_TABLE_SIZE; i += blockDim.x)
+    table[i] = (int16_t)peaq_synth_sine_entry((uint32_t)i);
+  if (threadIdx.x == 0) peaq_synth_pair_init(&sp, first_pair + blockIdx.y);
+  __syncthreads();
+  float* r = ref + (size_t)blockIdx.y * pair_stride;
+  float* t = test + (size_t)blockIdx.y * pair_stride;
+  const unsigned long long total = n_samples * (unsigned long long)channels;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long n = i / channels;
+    const int c = (int)(i - n * channels);
+    int32_t rv, tv;
+    peaq_synth_sample(&sp, table, n, c, &rv, &tv);
+    r[i] = (float)rv / 32768.0f;
+    t[i] = (float)tv / 32768.0f;
+  }
+}
+
+cudaError_t launch_synth_pairs(float* ref, float* test, size_t pair_stride, int n_pairs,
+                               unsigned long long first_pair_index, unsigned long long n_samples,
+                               int channels, cudaStream_t stream) {
+  if (n_pairs <= 0 || n_samples == 0) return cudaSuccess;
+  const unsigned long long total = n_samples * channels;
+  unsigned bx = (unsigned)std::min<unsigned long long>((total + 255) / 256, 1184);
+  for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+    const int np = std::min(65535, n_pairs - p0);
+    dim3 grid(bx, np);
+    synth_pairs_kernel<<<grid, 256, 0, stream>>>(ref + (size_t)p0 * pair_stride,
+                                                 test + (size_t)p0 * pair_stride, pair_stride,
+                                                 first_pair_index + p0, n_samples, channels);
+  }
+  return cudaGetLastError();
+}
+
+// number of FFT-clock frames for n samples per channel: do_processing
+// (gstpeaq.c:596-611) consumes 2048-sample frames every 1024 samples, do_flush
+// (:716-745) adds one zero-padded frame if anything is left
+static unsigned frames_for_samples(uint64_t n) {
+  uint64_t full = n >= kFftFrame ? (n - kFftFrame) / kFftStep + 1 : 0;
+  uint64_t left = n - full * kFftStep;
+  return (unsigned)(full + (left > 0 ? 1 : 0));
+}
+
+// ---------------------------------------------------------------------------
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int which;
+};
+
+struct Engine {
+  int device = 0;
+  bool advanced = false;
+  double level = 92.0;
+  DeviceTables* h_tables = nullptr;
+  DeviceTables* d_tables = nullptr;
+  cudaStream_t stream = nullptr;
+  double* d_records = nullptr;
+  size_t records_cap = 0;   // doubles
+  double* d_state = nullptr;
+  size_t state_cap = 0;
+  PairResult* d_results = nullptr;
+  unsigned long long* d_nsamples = nullptr;
+  unsigned* d_nframes = nullptr;
+  size_t pairs_cap = 0;
+  float* d_stage[2] = {nullptr, nullptr};
+  size_t stage_cap = 0;     // floats, each
+  std::vector<EventPair> events;
+  size_t events_used = 0;
+  double ms[5] = {0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+  bool keep_records = false;
+  RecordLayout last_layout = {};
+  size_t last_records_doubles = 0;
+  size_t record_budget_bytes = (size_t)16 << 30;
+
+  int init() {
+    PEAQ_CUDA(cudaSetDevice(device));
+    PEAQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    h_tables = new (std::nothrow) DeviceTables;
+    if (!h_tables) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
+    build_tables(h_tables, advanced, level);
+    PEAQ_CUDA(cudaMalloc(&d_tables, sizeof(DeviceTables)));
+    PEAQ_CUDA(cudaMemcpy(d_tables, h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice));
+    if (const char* env = std::getenv("PEAQ_B200_RECORD_BUDGET_MB")) {
+      const long mb = std::atol(env);
+      if (mb > 0) record_budget_bytes = (size_t)mb << 20;
+    }
+    return 0;
+  }
+
+  void destroy() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& e : events) {
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    cudaFree(d_records);
+    cudaFree(d_state);
+    cudaFree(d_results);
+    cudaFree(d_nsamples);
+    cudaFree(d_nframes);
+    cudaFree(d_stage[0]);
+    cudaFree(d_stage[1]);
+    cudaFree(d_tables);
+    if (stream) cudaStreamDestroy(stream);
+    delete h_tables;
+  }
+
+  int timer_begin(int which) {
+    if (events_used == events.size()) {
+      EventPair p;
+      p.which = which;
+      PEAQ_CUDA(cudaEventCreate(&p.a));
+      PEAQ_CUDA(cudaEventCreate(&p.b));
+      events.push_back(p);
+    }
+    events[events_used].which = which;
+    PEAQ_CUDA(cudaEventRecord(events[events_used].a, stream));
+    return 0;
+  }
+  int timer_end() {
+    PEAQ_CUDA(cudaEventRecord(events[events_used].b, stream));
+    events_used++;
+    return 0;
+  }
+  int timers_collect() {
+    for (size_t i = 0; i < events_used; i++) {
+      float t = 0;
+      PEAQ_CUDA(cudaEventElapsedTime(&t, events[i].a, events[i].b));
+      ms[events[i].which] += t;
+    }
+    events_used = 0;
+    return 0;
+  }
+
+  template <typename T>
+  int ensure(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*ptr) PEAQ_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    PEAQ_CUDA(cudaMalloc(ptr, need * sizeof(T)));
+    *cap = need;
+    return 0;
+  }
+
+  int ensure_pairs(size_t n_pairs, const StateLayout& S, bool preserve_state) {
+    if (n_pairs > pairs_cap) {
+      if (d_results) PEAQ_CUDA(cudaFree(d_results));
+      if (d_nsamples) PEAQ_CUDA(cudaFree(d_nsamples));
+      if (d_nframes) PEAQ_CUDA(cudaFree(d_nframes));
+      d_results = nullptr;
+      d_nsamples = nullptr;
+      d_nframes = nullptr;
+      PEAQ_CUDA(cudaMalloc(&d_results, n_pairs * sizeof(PairResult)));
+      PEAQ_CUDA(cudaMalloc(&d_nsamples, n_pairs * sizeof(unsigned long long)));
+      PEAQ_CUDA(cudaMalloc(&d_nframes, n_pairs * sizeof(unsigned)));
+      pairs_cap = n_pairs;
+    }
+    const size_t need = n_pairs * (size_t)S.stride;
+    if (need > state_cap) {
+      if (preserve_state) return fail(PEAQ_B200_ERR_INVALID, "state would be lost on growth");
+      int rc = ensure(&d_state, &state_cap, need);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+
+  // Runs frames of `n_pairs` pairs whose PCM is resident on the device.
+  // h_nframes[p] frames are processed for pair p, reading from sample 0 of the
+  // given buffers.  reset_state: start from fresh state (else continue).
+  int process_resident(const float* d_ref, const float* d_test, size_t pair_stride, int n_pairs,
+                       int C, const uint64_t* h_nsamples, const unsigned* h_nframes,
+                       bool reset_state, PairResult* h_out) {
+    const int B = h_tables->fft_bands;
+    const RecordLayout L = make_record_layout(C, B);
+    const StateLayout S = make_state_layout(C, B);
+    int rc = ensure_pairs((size_t)n_pairs, S, !reset_state);
+    if (rc) return rc;
+    unsigned max_frames = 0;
+    for (int p = 0; p < n_pairs; p++) max_frames = std::max(max_frames, h_nframes[p]);
+
+    std::vector<unsigned long long> ns(h_nsamples, h_nsamples + n_pairs);
+    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples, ns.data(), n_pairs * sizeof(unsigned long long),
+                              cudaMemcpyHostToDevice, stream));
+    PEAQ_CUDA(cudaMemcpyAsync(d_nframes, h_nframes, n_pairs * sizeof(unsigned),
+                              cudaMemcpyHostToDevice, stream));
+    if (reset_state) {
+      const size_t total = (size_t)n_pairs * S.stride;
+      const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+      init_state_kernel<<<blocks, 256, 0, stream>>>(d_state, S, n_pairs);
+      PEAQ_CUDA(cudaGetLastError());
+      launches++;
+    }
+
+    // frame chunking so that the records fit the budget
+    const size_t rec_bytes = (size_t)L.stride * sizeof(double);
+    size_t chunk = max_frames;
+    if (chunk == 0) chunk = 1;
+    if ((size_t)n_pairs * chunk * rec_bytes > record_budget_bytes) {
+      chunk = record_budget_bytes / ((size_t)n_pairs * rec_bytes);
+      if (chunk < 1) chunk = 1;
+    }
+    if (keep_records) chunk = std::max<size_t>(max_frames, 1);
+    rc = ensure(&d_records, &records_cap, (size_t)n_pairs * chunk * L.stride);
+    if (rc) return rc;
+
+    PcmView pcm;
+    pcm.ref = d_ref;
+    pcm.test = d_test;
+    pcm.pair_stride = pair_stride;
+    pcm.n_samples = d_nsamples;
+    pcm.n_frames = d_nframes;
+    pcm.channels = C;
+
+    unsigned first = 0;
+    do {
+      const unsigned n = (unsigned)std::min<size_t>(chunk, max_frames - first);
+      if (n > 0) {
+        if ((rc = timer_begin(1))) return rc;
+        PEAQ_CUDA(launch_fft_frames(d_tables, pcm, n_pairs, first, n, d_records, L, B, advanced, stream));
+        launches++;
+        if ((rc = timer_end())) return rc;
+      }
+      if ((rc = timer_begin(2))) return rc;
+      PEAQ_CUDA(launch_scan_basic(d_tables, d_records, L, d_nframes, first, n, d_state, S, d_results,
+                                  n_pairs, stream));
+      launches++;
+      if ((rc = timer_end())) return rc;
+      first += n;
+    } while (first < max_frames);
+    last_layout = L;
+    last_records_doubles = keep_records ? (size_t)n_pairs * chunk * L.stride : 0;
+
+    if (h_out) {
+      PEAQ_CUDA(cudaMemcpyAsync(h_out, d_results, n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost,
+                                stream));
+    }
+    PEAQ_CUDA(cudaStreamSynchronize(stream));
+    return timers_collect();
+  }
+};
+
+static int check_channels(int channels) {
+  if (channels < 1 || channels > kMaxChannels)
+    return fail(PEAQ_B200_ERR_INVALID, "channels must be 1 or 2");
+  return 0;
+}
+
+static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out) {
+  if (!e || !b || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  if (b->n_pairs <= 0) return fail(PEAQ_B200_ERR_INVALID, "n_pairs must be positive");
+  if (e->advanced) return fail(PEAQ_B200_ERR_INVALID, "advanced mode is not available in this build");
+  int rc = check_channels(b->channels);
+  if (rc) return rc;
+  if (!b->ref || !b->test) return fail(PEAQ_B200_ERR_INVALID, "null PCM pointer");
+  PEAQ_CUDA(cudaSetDevice(e->device));
+  const int C = b->channels;
+  const int n_pairs = b->n_pairs;
+  std::vector<uint64_t> ns(n_pairs);
+  std::vector<unsigned> nf(n_pairs);
+  uint64_t max_n = 0;
+  for (int p = 0; p < n_pairs; p++) {
+    ns[p] = b->n_samples ? b->n_samples[p] : b->n_samples_all;
+    if (ns[p] > ((uint64_t)UINT_MAX - 4) * kFftStep)
+      return fail(PEAQ_B200_ERR_INVALID, "item too long");
+    nf[p] = frames_for_samples(ns[p]);
+    max_n = std::max(max_n, ns[p]);
+    if (n_pairs > 1 && ns[p] * C > b->pair_stride)
+      return fail(PEAQ_B200_ERR_INVALID, "pair_stride smaller than an item");
+  }
+  for (int i = 0; i < 5; i++) e->ms[i] = 0;
+  cudaEvent_t t0, t1;
+  PEAQ_CUDA(cudaEventCreate(&t0));
+  PEAQ_CUDA(cudaEventCreate(&t1));
+  PEAQ_CUDA(cudaEventRecord(t0, e->stream));
+
+  PairResult* res = reinterpret_cast<PairResult*>(out);
+  if (b->on_device) {
+    if ((reinterpret_cast<uintptr_t>(b->ref) | reinterpret_cast<uintptr_t>(b->test)) & 15)
+      return fail(PEAQ_B200_ERR_INVALID, "device PCM pointers must be 16-byte aligned");
+    rc = e->process_resident(b->ref, b->test, b->pair_stride, n_pairs, C, ns.data(), nf.data(), true, res);
+    if (rc) return rc;
+  } else {
+    // host input: stage sub-batches of pairs through device buffers
+    const size_t stride = n_pairs > 1 ? b->pair_stride : (size_t)max_n * C;
+    const size_t stage_budget = (size_t)1 << 30;   // floats per staging buffer (4 GiB)
+    int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, stage_budget / std::max<size_t>(stride, 1)));
+    for (int p0 = 0; p0 < n_pairs; p0 += per) {
+      const int np = std::min(per, n_pairs - p0);
+      const size_t floats = (size_t)(np - 1) * stride + (size_t)max_n * C;
+      size_t cap0 = e->stage_cap, cap1 = e->stage_cap;
+      if ((rc = e->ensure(&e->d_stage[0], &cap0, std::max<size_t>(floats, 4)))) return rc;
+      if ((rc = e->ensure(&e->d_stage[1], &cap1, std::max<size_t>(floats, 4)))) return rc;
+      e->stage_cap = std::min(cap0, cap1);
+      if ((rc = e->timer_begin(3))) return rc;
+      if (floats) {
+        PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[0], b->ref + (size_t)p0 * stride, floats * sizeof(float),
+                                  cudaMemcpyHostToDevice, e->stream));
+        PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[1], b->test + (size_t)p0 * stride, floats * sizeof(float),
+                                  cudaMemcpyHostToDevice, e->stream));
+      }
+      if ((rc = e->timer_end())) return rc;
+      rc = e->process_resident(e->d_stage[0], e->d_stage[1], stride, np, C, ns.data() + p0, nf.data() + p0,
+                               true, res + p0);
+      if (rc) return rc;
+    }
+  }
+  PEAQ_CUDA(cudaEventRecord(t1, e->stream));
+  PEAQ_CUDA(cudaEventSynchronize(t1));
+  float t = 0;
+  PEAQ_CUDA(cudaEventElapsedTime(&t, t0, t1));
+  e->ms[0] = t;
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// session = one element instance
+
+struct Session {
+  int device = 0;
+  bool advanced = false;
+  double level = 92.0;
+  int channels = 0;
+  Engine* engine = nullptr;
+  bool started = false;          // state initialised on the device
+  std::vector<float> fifo[2];    // GstAdapter stand-ins (ref_adapter_fft / test_adapter_fft)
+  PairResult last = {};
+  bool have_result = false;
+
+  void drop_engine() {
+    if (engine) {
+      engine->destroy();
+      delete engine;
+      engine = nullptr;
+    }
+    started = false;
+    have_result = false;
+    fifo[0].clear();
+    fifo[1].clear();
+  }
+
+  int ensure_engine() {
+    if (engine) return 0;
+    engine = new (std::nothrow) Engine;
+    if (!engine) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
+    engine->device = device;
+    engine->advanced = advanced;
+    engine->level = level;
+    int rc = engine->init();
+    if (rc) {
+      engine->destroy();
+      delete engine;
+      engine = nullptr;
+    }
+    return rc;
+  }
+
+  // run `k` frames whose samples are the first (k-1)*1024+2048 of both FIFOs,
+  // or (padded != nullptr) one explicit zero-padded frame pair
+  int run_frames(unsigned k, const float* ref, const float* test, size_t n_samples) {
+    int rc = ensure_engine();
+    if (rc) return rc;
+    if (engine->advanced) return fail(PEAQ_B200_ERR_INVALID, "advanced mode is not available in this build");
+    PEAQ_CUDA(cudaSetDevice(device));
+    const size_t floats = n_samples * channels;
+    size_t cap0 = engine->stage_cap, cap1 = engine->stage_cap;
+    if ((rc = engine->ensure(&engine->d_stage[0], &cap0, std::max<size_t>(floats, 4)))) return rc;
+    if ((rc = engine->ensure(&engine->d_stage[1], &cap1, std::max<size_t>(floats, 4)))) return rc;
+    engine->stage_cap = std::min(cap0, cap1);
+    PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0], ref, floats * sizeof(float), cudaMemcpyHostToDevice,
+                              engine->stream));
+    PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[1], test, floats * sizeof(float), cudaMemcpyHostToDevice,
+                              engine->stream));
+    const uint64_t ns = n_samples;
+    rc = engine->process_resident(engine->d_stage[0], engine->d_stage[1], floats, 1, channels, &ns, &k,
+                                  !started, &last);
+    if (rc) return rc;
+    started = true;
+    have_result = true;
+    return 0;
+  }
+
+  // do_processing (gstpeaq.c:596-611)
+  int drain() {
+    const size_t fl = std::min(fifo[0].size(), fifo[1].size());
+    const size_t frame = (size_t)kFftFrame * channels, step = (size_t)kFftStep * channels;
+    if (fl < frame) return 0;
+    const unsigned k = (unsigned)((fl - frame) / step + 1);
+    const size_t n_samples = (size_t)(k - 1) * kFftStep + kFftFrame;
+    int rc = run_frames(k, fifo[0].data(), fifo[1].data(), n_samples);
+    if (rc) return rc;
+    for (int s = 0; s < 2; s++) fifo[s].erase(fifo[s].begin(), fifo[s].begin() + (size_t)k * step);
+    return 0;
+  }
+};
+
+}  // namespace peaq
+
+using namespace peaq;
+
+extern "C" {
+
+const char* peaq_b200_last_error(void) { return g_last_error.c_str(); }
+const char* peaq_b200_version(void) { return "peaq-b200 1"; }
+
+int peaq_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int peaq_b200_engine_create(peaq_b200_engine** out, int device, int advanced, double playback_level) {
+  if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (peaq_b200_device_count() <= device || device < 0)
+    return fail(PEAQ_B200_ERR_CUDA, "no such CUDA device (the engine has no CPU fallback)");
+  Engine* e = new (std::nothrow) Engine;
+  if (!e) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
+  e->device = device;
+  e->advanced = advanced != 0;
+  e->level = playback_level;
+  int rc = e->init();
+  if (rc) {
+    e->destroy();
+    delete e;
+    return rc;
+  }
+  *out = reinterpret_cast<peaq_b200_engine*>(e);
+  return 0;
+}
+
+int peaq_b200_engine_destroy(peaq_b200_engine* h) {
+  if (!h) return 0;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  e->destroy();
+  delete e;
+  return 0;
+}
+
+int peaq_b200_engine_run_batch(peaq_b200_engine* h, const peaq_b200_batch* batch, peaq_b200_result* out) {
+  return run_batch(reinterpret_cast<Engine*>(h), batch, out);
+}
+
+int peaq_b200_synth_pairs(int device, float* ref, float* test, size_t pair_stride, int32_t n_pairs,
+                          uint64_t first_pair, uint64_t n_samples, int32_t channels) {
+  if (!ref || !test) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  int rc = check_channels(channels);
+  if (rc) return rc;
+  if (n_pairs > 1 && n_samples * channels > pair_stride)
+    return fail(PEAQ_B200_ERR_INVALID, "pair_stride smaller than an item");
+  if (device < 0) {
+    static int16_t* table = nullptr;
+    if (!table) {
+      int16_t* t = new int16_t[PEAQ_SYNTH_TABLE_SIZE];
+      for (int i = 0; i < PEAQ_SYNTH_TABLE_SIZE; i++) t[i] = (int16_t)peaq_synth_sine_entry((uint32_t)i);
+      table = t;
+    }
+    for (int32_t p = 0; p < n_pairs; p++) {
+      PeaqSynthPair sp;
+      peaq_synth_pair_init(&sp, first_pair + p);
+      float* r = ref + (size_t)p * pair_stride;
+      float* t = test + (size_t)p * pair_stride;
+      for (uint64_t n = 0; n < n_samples; n++)
+        for (int c = 0; c < channels; c++) {
+          int32_t rv, tv;
+          peaq_synth_sample(&sp, table, n, c, &rv, &tv);
+          r[n * channels + c] = (float)rv / 32768.0f;
+          t[n * channels + c] = (float)tv / 32768.0f;
+        }
+    }
+    return 0;
+  }
+  PEAQ_CUDA(cudaSetDevice(device));
+  PEAQ_CUDA(launch_synth_pairs(ref, test, pair_stride, n_pairs, first_pair, n_samples, channels, 0));
+  PEAQ_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int peaq_b200_device_alloc(int device, size_t bytes, void** out) {
+  if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  PEAQ_CUDA(cudaSetDevice(device));
+  PEAQ_CUDA(cudaMalloc(out, bytes));
+  return 0;
+}
+int peaq_b200_device_free(int device, void* ptr) {
+  PEAQ_CUDA(cudaSetDevice(device));
+  PEAQ_CUDA(cudaFree(ptr));
+  return 0;
+}
+int peaq_b200_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
+  PEAQ_CUDA(cudaSetDevice(device));
+  PEAQ_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+int peaq_b200_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
+  PEAQ_CUDA(cudaSetDevice(device));
+  PEAQ_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int peaq_b200_host_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  PEAQ_CUDA(cudaMallocHost(out, bytes));
+  return 0;
+}
+int peaq_b200_host_free_pinned(void* ptr) {
+  PEAQ_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
+double peaq_b200_engine_last_ms(const peaq_b200_engine* h, int which) {
+  const Engine* e = reinterpret_cast<const Engine*>(h);
+  if (!e || which < 0 || which > 4) return -1.;
+  return e->ms[which];
+}
+
+uint64_t peaq_b200_engine_launch_count(const peaq_b200_engine* h) {
+  const Engine* e = reinterpret_cast<const Engine*>(h);
+  return e ? e->launches : 0;
+}
+
+int peaq_b200_engine_keep_records(peaq_b200_engine* h, int enable) {
+  if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  reinterpret_cast<Engine*>(h)->keep_records = enable != 0;
+  return 0;
+}
+
+int peaq_b200_engine_record_layout(const peaq_b200_engine* h, int32_t* out) {
+  if (!h || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  const RecordLayout& L = reinterpret_cast<const Engine*>(h)->last_layout;
+  out[0] = L.C; out[1] = L.B; out[2] = L.off_noise; out[3] = L.off_ehs; out[4] = L.off_snr;
+  out[5] = L.off_ints; out[6] = L.stride; out[7] = 0; out[8] = 0;
+  return 0;
+}
+
+int peaq_b200_engine_copy_records(peaq_b200_engine* h, double* dst, size_t max_doubles, size_t* n_doubles) {
+  if (!h || !dst) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  const size_t n = std::min(max_doubles, e->last_records_doubles);
+  PEAQ_CUDA(cudaSetDevice(e->device));
+  if (n) PEAQ_CUDA(cudaMemcpy(dst, e->d_records, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_doubles) *n_doubles = n;
+  return 0;
+}
+
+int peaq_b200_engine_table(const peaq_b200_engine* h, int model, int which, double* out) {
+  if (!h || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  const DeviceTables& t = *reinterpret_cast<const Engine*>(h)->h_tables;
+  const BandTables& b = model ? t.fb : t.fft;
+  for (int i = 0; i < b.B; i++) {
+    double v;
+    switch (which) {
+      case 0: v = b.fc[i]; break;
+      case 1: v = b.internal_noise[i]; break;
+      case 2: v = b.a_ear[i]; break;
+      case 3: v = b.ethres[i]; break;
+      case 4: v = b.thres[i]; break;
+      case 5: v = b.loudfac[i]; break;
+      case 14: v = b.a_proc[i]; break;
+      default:
+        if (model) return fail(PEAQ_B200_ERR_INVALID, "no such table");
+        switch (which) {
+          case 6: v = t.maskdiff[i]; break;
+          case 7: v = t.aUC[i]; break;
+          case 8: v = t.gIL[i]; break;
+          case 9: v = t.spread_norm[i]; break;
+          case 10: v = t.band_wl[i]; break;
+          case 11: v = t.band_wu[i]; break;
+          case 12: v = t.band_lo[i]; break;
+          case 13: v = t.band_hi[i]; break;
+          default: return fail(PEAQ_B200_ERR_INVALID, "no such table");
+        }
+    }
+    out[i] = v;
+  }
+  return b.B;
+}
+
+int peaq_b200_session_create(peaq_b200_session** out, int device) {
+  if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (peaq_b200_device_count() <= device || device < 0)
+    return fail(PEAQ_B200_ERR_CUDA, "no such CUDA device (the engine has no CPU fallback)");
+  Session* s = new (std::nothrow) Session;
+  if (!s) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
+  s->device = device;
+  *out = reinterpret_cast<peaq_b200_session*>(s);
+  return 0;
+}
+
+int peaq_b200_session_destroy(peaq_b200_session* h) {
+  if (!h) return 0;
+  Session* s = reinterpret_cast<Session*>(h);
+  s->drop_engine();
+  delete s;
+  return 0;
+}
+
+int peaq_b200_session_set_advanced(peaq_b200_session* h, int advanced) {
+  if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  Session* s = reinterpret_cast<Session*>(h);
+  s->drop_engine();
+  s->advanced = advanced != 0;
+  return 0;
+}
+
+int peaq_b200_session_set_playback_level(peaq_b200_session* h, double level_db) {
+  if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  if (!(level_db >= 0. && level_db <= 130.)) return fail(PEAQ_B200_ERR_INVALID, "playback level out of range");
+  Session* s = reinterpret_cast<Session*>(h);
+  if (s->started) return fail(PEAQ_B200_ERR_INVALID, "playback level cannot change mid-stream");
+  s->drop_engine();
+  s->level = level_db;
+  return 0;
+}
+
+int peaq_b200_session_get_playback_level(const peaq_b200_session* h, double* level_db) {
+  if (!h || !level_db) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  *level_db = reinterpret_cast<const Session*>(h)->level;
+  return 0;
+}
+
+int peaq_b200_session_set_channels(peaq_b200_session* h, int channels) {
+  if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  int rc = check_channels(channels);
+  if (rc) return rc;
+  Session* s = reinterpret_cast<Session*>(h);
+  // set_caps frees and reallocates all per-channel state (gstpeaq.c:575-586)
+  s->started = false;
+  s->have_result = false;
+  s->fifo[0].clear();
+  s->fifo[1].clear();
+  s->channels = channels;
+  return 0;
+}
+
+int peaq_b200_session_push(peaq_b200_session* h, int pad, const float* data, size_t n) {
+  if (!h || (n && !data)) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  if (pad != PEAQ_B200_PAD_REF && pad != PEAQ_B200_PAD_TEST) return fail(PEAQ_B200_ERR_INVALID, "bad pad");
+  Session* s = reinterpret_cast<Session*>(h);
+  if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
+  s->fifo[pad].insert(s->fifo[pad].end(), data, data + n * s->channels);
+  return s->drain();
+}
+
+int peaq_b200_session_finish(peaq_b200_session* h) {
+  if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  Session* s = reinterpret_cast<Session*>(h);
+  if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
+  int rc = s->drain();
+  if (rc) return rc;
+  // do_flush (gstpeaq.c:716-745): one zero-padded frame from whatever is left
+  if (!s->fifo[0].empty() || !s->fifo[1].empty()) {
+    const size_t frame = (size_t)kFftFrame * s->channels;
+    std::vector<float> pr(frame, 0.f), pt(frame, 0.f);
+    const size_t nr = std::min(s->fifo[0].size(), frame), nt = std::min(s->fifo[1].size(), frame);
+    std::copy(s->fifo[0].begin(), s->fifo[0].begin() + nr, pr.begin());
+    std::copy(s->fifo[1].begin(), s->fifo[1].begin() + nt, pt.begin());
+    rc = s->run_frames(1, pr.data(), pt.data(), kFftFrame);
+    if (rc) return rc;
+    s->fifo[0].erase(s->fifo[0].begin(), s->fifo[0].begin() + nr);
+    s->fifo[1].erase(s->fifo[1].begin(), s->fifo[1].begin() + nt);
+  }
+  return 0;
+}
+
+int peaq_b200_session_get_result(peaq_b200_session* h, peaq_b200_result* out) {
+  if (!h || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  Session* s = reinterpret_cast<Session*>(h);
+  if (!s->have_result) {
+    // no frame processed yet: the reference would evaluate empty accumulators
+    // (0/0); report that state without touching the GPU
+    std::memset(out, 0, sizeof *out);
+    const double nanv = std::nan("");
+    out->odg = out->di = out->totalsnr = nanv;
+    out->n_movs = s->advanced ? 5 : 11;
+    for (int i = 0; i < out->n_movs; i++) out->movs[i] = nanv;
+    out->loudness_reached_frame = UINT_MAX;
+    return 0;
+  }
+  std::memcpy(out, &s->last, sizeof *out);
+  return 0;
+}
+
+}  // extern "C"

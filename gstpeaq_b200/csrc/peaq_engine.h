@@ -1,0 +1,118 @@
+// Internal C++ interface of the PEAQ CUDA engine (not part of the C ABI).
+//
+// Data flow (DESIGN.md has the long version):
+//   PCM in HBM --K1 fft_frames--> per-frame records --K2 scan_basic--> pair state/result
+// K1 is frame-parallel and stateless; K2 carries every recurrence of the
+// reference (time smearing, level adapter, modulation, accumulators) in
+// registers across its frame loop and persists it in `PairState` memory between
+// chunks, so hour-long items and streaming sessions run as a sequence of chunks.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "peaq_tables.h"
+
+namespace peaq {
+
+constexpr int kMaxChannels = 2;
+constexpr int kNumAcc = 11;        // accumulator slots (11 basic MOVs; 5 used in advanced)
+constexpr int kAccFields = 8;      // num, den, x0, x1, x2, saved num, saved den, saved max
+constexpr int kBandStateFields = 14;
+
+// Layout of one per-frame record written by K1 and read by K2 (units: doubles).
+struct RecordLayout {
+  int C;           // channels
+  int B;           // FFT bands
+  int off_noise;   // noise_in_bands[c][b]
+  int off_ehs;     // ehs[c]
+  int off_snr;     // signal, noise partial sums of this frame
+  int off_ints;    // int32: flags, then (bw_ref, bw_test) per channel
+  int stride;      // doubles per record
+};
+
+inline RecordLayout make_record_layout(int C, int B) {
+  RecordLayout L;
+  L.C = C;
+  L.B = B;
+  L.off_noise = 2 * C * B;
+  L.off_ehs = L.off_noise + C * B;
+  L.off_snr = L.off_ehs + C;
+  L.off_ints = L.off_snr + 2;
+  L.stride = L.off_ints + (1 + 2 * C + 1) / 2;
+  return L;
+}
+
+constexpr int kRecFlagAbove = 1;     // is_frame_above_threshold (gstpeaq.c:1081-1099)
+constexpr int kRecFlagEhsValid = 2;  // any energy flag set (movs.c:1375-1381)
+
+// Per-pair recurrent state, basic mode (units: doubles unless noted).
+struct StateLayout {
+  int C, B;
+  int off_band;    // [field][c][b], kBandStateFields fields
+  int off_acc;     // [c][kNumAcc][kAccFields]
+  int off_scalar;  // signal energy, noise energy
+  int off_ints;    // int32: status, frame counter, loudness-reached frame, fb frame counter, fb status
+  int stride;
+};
+
+inline StateLayout make_state_layout(int C, int B) {
+  StateLayout S;
+  S.C = C;
+  S.B = B;
+  S.off_band = 0;
+  S.off_acc = kBandStateFields * C * B;
+  S.off_scalar = S.off_acc + C * kNumAcc * kAccFields;
+  S.off_ints = S.off_scalar + 2;
+  S.stride = S.off_ints + 4;
+  return S;
+}
+
+// Mirrors peaq_b200_result of the C ABI (include/peaq_b200.h).
+struct PairResult {
+  double odg;
+  double di;
+  double totalsnr;
+  double movs[11];
+  int32_t n_movs;
+  uint32_t frames_fft;
+  uint32_t frames_fb;
+  uint32_t loudness_reached_frame;
+};
+
+// View of resident PCM: pair p's ref signal starts at ref + p*pair_stride
+// floats, interleaved [sample][channel]; samples >= n_samples[p] read as zero.
+struct PcmView {
+  const float* ref;
+  const float* test;
+  size_t pair_stride;
+  const unsigned long long* n_samples;  // device, per pair
+  const unsigned* n_frames;             // device, per pair: FFT-clock frames to run
+  int channels;
+};
+
+struct LaunchStats {
+  unsigned long long launches;
+};
+
+// K0: synthetic (ref,test) pairs generated in place (bench/test input only).
+cudaError_t launch_synth_pairs(float* ref, float* test, size_t pair_stride, int n_pairs,
+                               unsigned long long first_pair_index, unsigned long long n_samples,
+                               int channels, cudaStream_t stream);
+
+// K1: frames [first_frame, first_frame + n_chunk_frames) of every pair.
+cudaError_t launch_fft_frames(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
+                              unsigned first_frame, unsigned n_chunk_frames, double* records,
+                              RecordLayout L, int fft_bands, bool advanced, cudaStream_t stream);
+
+// K2 (basic): consumes the records of one chunk, updates the state, writes results.
+cudaError_t launch_scan_basic(const DeviceTables* d_tables, const double* records, RecordLayout L,
+                              const unsigned* n_frames, unsigned first_frame,
+                              unsigned n_chunk_frames, double* state, StateLayout S,
+                              PairResult* results, int n_pairs, cudaStream_t stream);
+
+size_t fft_frames_smem_bytes(int channels);
+
+}  // namespace peaq
