@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "peaq_b200_memcpy_h2d", "peaq_b200_memcpy_d2h", "peaq_b200_host_alloc_pinned",
     "peaq_b200_host_free_pinned", "peaq_b200_engine_last_ms", "peaq_b200_engine_launch_count",
     "peaq_b200_engine_keep_records", "peaq_b200_engine_record_layout",
-    "peaq_b200_engine_copy_records", "peaq_b200_engine_table",
+    "peaq_b200_engine_copy_records", "peaq_b200_table",
     "peaq_b200_session_create", "peaq_b200_session_destroy", "peaq_b200_session_set_advanced",
     "peaq_b200_session_set_playback_level", "peaq_b200_session_get_playback_level",
     "peaq_b200_session_set_channels", "peaq_b200_session_push", "peaq_b200_session_finish",
@@ -120,7 +120,7 @@ def load_library():
     L.peaq_b200_engine_record_layout.argtypes = [C.c_void_p, C.c_void_p]
     L.peaq_b200_engine_copy_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t,
                                                 C.POINTER(C.c_size_t)]
-    L.peaq_b200_engine_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.peaq_b200_table.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.peaq_b200_session_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.peaq_b200_session_destroy.argtypes = [C.c_void_p]
     L.peaq_b200_session_set_advanced.argtypes = [C.c_void_p, C.c_int]
@@ -161,6 +161,14 @@ def synth_pairs_host(first_pair, n_pairs, n_samples, channels=2):
     _check(L.peaq_b200_synth_pairs(-1, ref.ctypes.data, test.ctypes.data, n_samples * channels,
                                    n_pairs, first_pair, n_samples, channels))
     return ref, test
+
+
+def table(advanced, model, which, playback_level=92.0):
+    """Constant table of the engine (host code; see peaq_b200_table)."""
+    buf = np.zeros(128, dtype=np.float64)
+    n = load_library().peaq_b200_table(int(advanced), float(playback_level), model, which,
+                                       buf.ctypes.data)
+    return buf[:max(n, 0)].copy()
 
 
 class DeviceBuffer:
@@ -277,12 +285,6 @@ class Engine:
             "bw_test": ints[:, :, 2:2 + 2 * Cn:2],
         }
 
-    def table(self, model, which):
-        buf = np.zeros(128, dtype=np.float64)
-        n = self.lib.peaq_b200_engine_table(self.h, model, which, buf.ctypes.data)
-        if n < 0:
-            _check(n)
-        return buf[:n].copy()
 
 
 class Peaq:

@@ -620,9 +620,13 @@ int peaq_b200_engine_copy_records(peaq_b200_engine* h, double* dst, size_t max_d
   return 0;
 }
 
-int peaq_b200_engine_table(const peaq_b200_engine* h, int model, int which, double* out) {
-  if (!h || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
-  const DeviceTables& t = *reinterpret_cast<const Engine*>(h)->h_tables;
+int peaq_b200_table(int advanced, double playback_level, int model, int which, double* out) {
+  if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  DeviceTables* tp = new (std::nothrow) DeviceTables;
+  if (!tp) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
+  build_tables(tp, advanced != 0, playback_level);
+  struct Guard { DeviceTables* p; ~Guard() { delete p; } } guard{tp};
+  const DeviceTables& t = *tp;
   const BandTables& b = model ? t.fb : t.fft;
   for (int i = 0; i < b.B; i++) {
     double v;

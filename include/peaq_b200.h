@@ -117,9 +117,10 @@ int peaq_b200_engine_keep_records(peaq_b200_engine *e, int enable);
 int peaq_b200_engine_record_layout(const peaq_b200_engine *e, int32_t *layout9);
 int peaq_b200_engine_copy_records(peaq_b200_engine *e, double *dst, size_t max_doubles,
                                   size_t *n_doubles);
-/* constant tables (same `model`/`which` numbering as the oracle's
+/* constant tables of the engine for a mode / playback level (host code, no
+ * GPU needed; same `model`/`which` numbering as the oracle's
  * peaq_oracle_table); returns the count, < 0 on error */
-int peaq_b200_engine_table(const peaq_b200_engine *e, int model, int which, double *out);
+int peaq_b200_table(int advanced, double playback_level, int model, int which, double *out);
 
 /* ------------------------------------------------------------------------
  * Session: one element instance (struct _GstPeaq, gstpeaq.c:110-139).

@@ -1,0 +1,34 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # build the CPU checker and the engine library if they are missing (the
+    # prebuilt files normally travel with the snapshot)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libpeaq_oracle.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    if not os.path.exists(os.path.join(ROOT, "gstpeaq_b200", "libpeaq_b200.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "gstpeaq_b200", "csrc")])
+    if (not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpeaq_ref.so"))
+            and os.path.isdir("/root/reference/src")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+
+
+@pytest.fixture(scope="session")
+def golden_ref_outputs():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_outputs.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_vectors():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "testpeaq_vectors.npz")))

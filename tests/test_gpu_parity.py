@@ -1,0 +1,225 @@
+"""GPU: the CUDA engine against the CPU oracle, through the C ABI.
+
+Bar (SURVEY 8d / BASELINE north star): integer-valued quantities exact (frame
+counts, per-frame bandwidth bins, above-threshold / EHS-valid flags,
+loudness-reached frame); floating MOVs rel <= 1e-6; |dODG|, |dDI| <= 1e-4
+(expected ~1e-12: the engine is FP64 end to end); known-answer ODGs print
+identically at %.3f."""
+import math
+
+import numpy as np
+import pytest
+
+import gstpeaq_b200 as G
+import refharness as H
+from signals import golden_cases, noise_pair, synth_pair
+
+pytestmark = pytest.mark.gpu
+
+MOV_RTOL = 1e-6
+ODG_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = G.Engine(0, advanced=False)
+    yield e
+    e.close()
+
+
+def check_result(got, want, what):
+    """got: one row of the engine's result array; want: oracle/reference dict"""
+    assert int(got["frames_fft"]) == want["frames_fft"], what
+    assert int(got["loudness_reached_frame"]) == want["loudness_reached_frame"], what
+    n = len(want["movs"])
+    assert int(got["n_movs"]) == n
+    np.testing.assert_allclose(got["movs"][:n], want["movs"], rtol=MOV_RTOL, atol=1e-9, equal_nan=True,
+                               err_msg=what)
+    for k in ("di", "odg"):
+        if math.isnan(want[k]):
+            assert math.isnan(got[k]), what
+        else:
+            assert abs(got[k] - want[k]) <= ODG_ATOL, (what, k, got[k], want[k])
+    if math.isfinite(want["totalsnr"]):
+        assert abs(got["totalsnr"] - want["totalsnr"]) < 1e-6, what
+
+
+def test_device_generator_is_bit_identical_to_host_generator():
+    L = G.load_library()
+    n_pairs, ns, ch = 3, 30000, 2
+    dref = G.DeviceBuffer(0, n_pairs * ns * ch * 4)
+    dtest = G.DeviceBuffer(0, n_pairs * ns * ch * 4)
+    G._check(L.peaq_b200_synth_pairs(0, dref.ptr, dtest.ptr, ns * ch, n_pairs, 5, ns, ch))
+    hr = np.zeros((n_pairs, ns * ch), np.float32)
+    ht = np.zeros_like(hr)
+    G._check(L.peaq_b200_memcpy_d2h(0, hr.ctypes.data, dref.ptr, hr.nbytes))
+    G._check(L.peaq_b200_memcpy_d2h(0, ht.ctypes.data, dtest.ptr, ht.nbytes))
+    r2, t2 = G.synth_pairs_host(5, n_pairs, ns, ch)
+    np.testing.assert_array_equal(hr, r2)
+    np.testing.assert_array_equal(ht, t2)
+
+
+def test_known_answer_odgs_print_like_the_reference(engine):
+    """runtest-1.0.sh:18,28,38,48"""
+    cases = golden_cases()
+    for name, want in (("kat_sine_sine_mono", "0.171"), ("kat_saw_tri_mono", "-2.007"),
+                       ("kat_saw_tri_stereo", "-2.007")):
+        ref, test, ch = cases[name]
+        out = engine.run_host(ref, test, ch)
+        assert "%.3f" % out["odg"][0] == want, name
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases().keys()))
+def test_batch_matches_committed_reference_outputs(engine, golden_ref_outputs, name):
+    """fixtures = outputs of the reference's own C code (tests/golden/make_golden.py)"""
+    ref, test, ch = golden_cases()[name]
+    v = golden_ref_outputs[name + "|basic"]
+    n = int(v[6])
+    want = {"odg": v[0], "di": v[1], "totalsnr": v[2], "frames_fft": int(v[3]),
+            "loudness_reached_frame": int(v[5]), "movs": v[7:7 + n]}
+    out = engine.run_host(ref, test, ch)
+    check_result(out[0], want, name)
+
+
+@pytest.mark.parametrize("name", ["synth0_stereo", "noise_silence_stereo", "kat_saw_tri_mono", "synth5_mono"])
+def test_per_frame_records_match_oracle(engine, name):
+    ref, test, ch = golden_cases()[name]
+    nf = G.frames_for_samples(ref.size // ch)
+    o = H.OraclePeaq(False, 92.0, ch, fft_trace=nf)
+    o.run(ref, test)
+    tr = o.fft_trace
+    engine.keep_records(True)
+    try:
+        engine.run_host(ref, test, ch)
+        rec = engine.records(1, nf)
+    finally:
+        engine.keep_records(False)
+    B = 109
+    # integer-valued: exact
+    np.testing.assert_array_equal(rec["flags"][0] & 1, tr["above_threshold"])
+    np.testing.assert_array_equal((rec["flags"][0] >> 1) & 1, tr["ehs_valid"])
+    np.testing.assert_array_equal(rec["bw_ref"][0], tr["bw_ref"][:, :ch])
+    np.testing.assert_array_equal(rec["bw_test"][0], tr["bw_test"][:, :ch])
+    # floating point
+    np.testing.assert_allclose(rec["unsmeared"][0], tr["unsmeared"][:, :, :ch, :B], rtol=1e-10)
+    # noise in bands = P_ref - 2 sqrt(P_ref P_test) + P_test cancels heavily: compare
+    # against the band's signal power scale as well
+    np.testing.assert_allclose(rec["noise_in_bands"][0], tr["noise_in_bands"][:, :ch, :B], rtol=1e-4, atol=1e-9)
+    valid = tr["ehs_valid"].astype(bool)
+    np.testing.assert_allclose(rec["ehs"][0][valid], tr["ehs"][valid][:, :ch], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(np.cumsum(rec["snr"][0][:, 0]), tr["signal_energy"], rtol=1e-12)
+    np.testing.assert_allclose(np.cumsum(rec["snr"][0][:, 1]), tr["noise_energy"], rtol=1e-12)
+
+
+def test_batch_of_ragged_synthetic_pairs_matches_oracle(engine):
+    """one call, pairs of different lengths (incl. empty and sub-frame items)"""
+    ch = 2
+    lengths = [48000, 30001, 2048, 1, 0, 70000, 4096 + 512, 1023]
+    stride = max(lengths) * ch
+    ref = np.zeros((len(lengths), stride), np.float32)
+    test = np.zeros_like(ref)
+    for p, n in enumerate(lengths):
+        if n:
+            r, t = synth_pair(100 + p, n, ch)
+            ref[p, :n * ch] = r
+            test[p, :n * ch] = t
+    out = engine.run_host(ref, test, ch, n_samples=np.array(lengths, np.uint64))
+    for p, n in enumerate(lengths):
+        want = H.oracle_run_pair(ref[p, :n * ch], test[p, :n * ch], ch)
+        check_result(out[p], want, "pair %d len %d" % (p, n))
+
+
+def test_chunked_frame_loop_is_bit_identical(engine, monkeypatch):
+    """records budget forces several K1/K2 chunks: the recurrent state handed
+    over in memory must give bit-identical results to the single-chunk run"""
+    ch = 2
+    r, t = G.synth_pairs_host(40, 6, 60000, ch)
+    a = engine.run_host(r, t, ch)
+    monkeypatch.setenv("PEAQ_B200_RECORD_BUDGET_MB", "1")
+    e2 = G.Engine(0, advanced=False)
+    try:
+        b = e2.run_host(r, t, ch)
+    finally:
+        e2.close()
+    for k in ("odg", "di", "totalsnr", "movs", "frames_fft", "loudness_reached_frame"):
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_device_resident_batch_equals_host_batch(engine):
+    L = G.load_library()
+    n_pairs, ns, ch = 5, 40000, 2
+    dref = G.DeviceBuffer(0, n_pairs * ns * ch * 4)
+    dtest = G.DeviceBuffer(0, n_pairs * ns * ch * 4)
+    G._check(L.peaq_b200_synth_pairs(0, dref.ptr, dtest.ptr, ns * ch, n_pairs, 9, ns, ch))
+    a = engine.run_device(dref.ptr, dtest.ptr, n_pairs, ns * ch, ch, ns)
+    r, t = G.synth_pairs_host(9, n_pairs, ns, ch)
+    b = engine.run_host(r, t, ch)
+    np.testing.assert_array_equal(a["odg"], b["odg"])
+    np.testing.assert_array_equal(a["movs"], b["movs"])
+    assert engine.launch_count() > 0
+
+
+def test_session_streaming_matches_oracle_with_arbitrary_buffers():
+    """element surface: caps, chain on both pads with arbitrary buffer sizes,
+    unequal stream lengths, stop -> odg/di (gstpeaq.c:614-661, :716-745, :764-778)"""
+    rng = np.random.default_rng(3)
+    ch = 2
+    ref, test = synth_pair(21, 30000, ch)
+    test = test[:ch * 29000]
+    o = H.OraclePeaq(False, 92.0, ch)
+    p = G.Peaq(0, console_output=False)
+    p.set_caps(ch)
+    assert math.isnan(p.odg)          # nothing processed yet: 0/0 like the reference
+    pr = pt = 0
+    while pr < ref.size or pt < test.size:
+        a = ch * int(rng.integers(1, 4000))
+        b = ch * int(rng.integers(1, 4000))
+        cr, ct = ref[pr:pr + a], test[pt:pt + b]
+        p.chain_ref(cr)
+        p.chain_test(ct)
+        o.push(cr, ct)
+        pr += a
+        pt += b
+        mid = p.result()
+        want_mid = o.result()
+        assert mid["frames_fft"] == want_mid["frames_fft"]
+    res = p.stop()
+    o.finish()
+    want = o.result()
+    got = {"frames_fft": res["frames_fft"], "loudness_reached_frame": res["loudness_reached_frame"],
+           "n_movs": 11, "movs": np.concatenate([res["movs"], np.zeros(0)]), "di": res["di"], "odg": res["odg"],
+           "totalsnr": res["totalsnr"]}
+    check_result(got, want, "session")
+    assert abs(p.odg - want["odg"]) < ODG_ATOL and abs(p.di - want["di"]) < ODG_ATOL
+    p.close()
+
+
+def test_session_console_output_format(capsys):
+    ref, test, ch = golden_cases()["kat_saw_tri_mono"]
+    p = G.Peaq(0, console_output=True)
+    p.set_caps(ch)
+    p.chain_ref(ref)
+    p.chain_test(test)
+    p.stop()
+    out = capsys.readouterr().out
+    assert out.splitlines()[0].startswith("   BandwidthRefB: 921.000000")
+    assert out.splitlines()[-1] == "Objective Difference Grade: -2.007"
+    p.close()
+
+
+def test_linearity_property_playback_level():
+    """size-independent property: +6.0206 dB playback level == input scaled by 2
+    (level enters only through the FFT level factor, fftearmodel.c:304-314)"""
+    ch = 2
+    r, t = G.synth_pairs_host(77, 2, 40000, ch)
+    e1 = G.Engine(0, False, 92.0 + 20 * math.log10(2.0))
+    e2 = G.Engine(0, False, 92.0)
+    try:
+        a = e1.run_host(r * np.float32(0.5), t * np.float32(0.5), ch)
+        b = e2.run_host(r, t, ch)
+    finally:
+        e1.close()
+        e2.close()
+    # thresholds on raw samples (above-threshold, energy flag) are level independent
+    # here because the signals are loud; MOVs agree to rounding
+    np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9)

@@ -1,0 +1,89 @@
+"""CPU: host-side logic of the product -- the C-ABI library loads and exports
+every symbol of include/peaq_b200.h, its constant tables equal the oracle's,
+the integer generator is deterministic, and compute calls fail loudly without
+a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gstpeaq_b200 as G
+import refharness as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "peaq_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(peaq_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(G.ABI_SYMBOLS)
+    L = G.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.peaq_b200_version().startswith(b"peaq-b200")
+
+
+def test_result_struct_layout():
+    assert G.C.sizeof(G.Result) == 128 == G.RESULT_DTYPE.itemsize
+
+
+def test_frames_for_samples_matches_reference_framing():
+    # gstpeaq.c:596-611 + :716-745 (10 s -> 468, 1 h -> 168750)
+    assert G.frames_for_samples(480000) == 468
+    assert G.frames_for_samples(172800000) == 168750
+    assert G.frames_for_samples(131072) == 128
+    assert G.frames_for_samples(0) == 0
+    assert G.frames_for_samples(1) == 1
+    assert G.frames_for_samples(2048) == 2
+    assert G.frames_for_samples(2047) == 1
+    for n in (1500, 2049, 3072, 3073, 48765):
+        o = H.oracle_run_pair(np.zeros(n, np.float32), np.zeros(n, np.float32), 1)
+        assert o["frames_fft"] == G.frames_for_samples(n)
+
+
+@pytest.mark.skipif(G.device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(G.PeaqError, match="no CPU fallback"):
+        G.Engine(0)
+    with pytest.raises(G.PeaqError, match="no CPU fallback"):
+        G.Peaq(0)
+
+
+def test_synth_generator_is_deterministic_and_random_access():
+    a_r, a_t = G.synth_pairs_host(3, 2, 5000, 2)
+    b_r, b_t = G.synth_pairs_host(4, 1, 5000, 2)
+    np.testing.assert_array_equal(a_r[1], b_r[0])
+    np.testing.assert_array_equal(a_t[1], b_t[0])
+    # 16-bit grid, exact /32768
+    assert np.all(a_r * 32768 == np.round(a_r * 32768))
+    assert np.abs(a_r).max() < 1.0 and np.abs(a_r).max() > 0.05
+    assert not np.array_equal(a_r[0], a_t[0])
+    m_r, _ = G.synth_pairs_host(3, 1, 5000, 1)
+    np.testing.assert_array_equal(m_r[0], a_r[0][0::2])   # channel 0 is the mono signal
+
+
+def test_synth_pairs_have_finite_spread_odg():
+    """SURVEY 8d acceptance: every synthetic pair gives a finite ODG"""
+    odgs = []
+    for p in range(14):
+        r, t = G.synth_pairs_host(p, 1, 48000, 2)
+        o = H.oracle_run_pair(r[0], t[0], 2)
+        assert np.isfinite(o["odg"]), p
+        odgs.append(o["odg"])
+    assert min(odgs) < -1.5 and max(odgs) > -0.6
+
+
+def test_engine_tables_match_oracle_tables():
+    """every table the kernels read equals the oracle's (built by the same
+    formulas as the reference's constructors)"""
+    for advanced in (0, 1):
+        o = H.OraclePeaq(bool(advanced), 92.0, 1)
+        for model in (0, 1):
+            for which in range(15):
+                want = o.table(model, which)
+                got = G.table(advanced, model, which)
+                assert got.size == want.size, (advanced, model, which)
+                if want.size:
+                    np.testing.assert_allclose(got, want, rtol=2e-15, atol=0,
+                                               err_msg=str((advanced, model, which)))
