@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "peaq_b200_memcpy_h2d", "peaq_b200_memcpy_d2h", "peaq_b200_host_alloc_pinned",
     "peaq_b200_host_free_pinned", "peaq_b200_engine_last_ms", "peaq_b200_engine_launch_count",
     "peaq_b200_engine_keep_records", "peaq_b200_engine_record_layout",
-    "peaq_b200_engine_copy_records", "peaq_b200_table",
+    "peaq_b200_engine_copy_records", "peaq_b200_engine_copy_fb_debug", "peaq_b200_table",
     "peaq_b200_session_create", "peaq_b200_session_destroy", "peaq_b200_session_set_advanced",
     "peaq_b200_session_set_playback_level", "peaq_b200_session_get_playback_level",
     "peaq_b200_session_set_channels", "peaq_b200_session_push", "peaq_b200_session_finish",
@@ -120,6 +120,8 @@ def load_library():
     L.peaq_b200_engine_record_layout.argtypes = [C.c_void_p, C.c_void_p]
     L.peaq_b200_engine_copy_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t,
                                                 C.POINTER(C.c_size_t)]
+    L.peaq_b200_engine_copy_fb_debug.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t,
+                                                 C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
     L.peaq_b200_table.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.peaq_b200_session_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.peaq_b200_session_destroy.argtypes = [C.c_void_p]
@@ -264,6 +266,21 @@ class Engine:
 
     def keep_records(self, enable=True):
         _check(self.lib.peaq_b200_engine_keep_records(self.h, int(enable)))
+
+    def fb_debug(self, n_pairs, channels):
+        """Advanced mode taps of the last run (needs keep_records(True)):
+        (exc [pair, frame, stream, U|E, 40], movs [pair, frame, channel, 8])"""
+        cap = 1 << 26
+        buf = np.zeros(cap, dtype=np.float64)
+        n = C.c_size_t()
+        fr = C.c_uint32()
+        _check(self.lib.peaq_b200_engine_copy_fb_debug(self.h, buf.ctypes.data, cap, C.byref(n),
+                                                       C.byref(fr)))
+        F = fr.value
+        n_exc = n_pairs * F * 2 * channels * 2 * 40
+        exc = buf[:n_exc].reshape(n_pairs, F, 2 * channels, 2, 40)
+        movs = buf[n_exc:n_exc + n_pairs * F * channels * 8].reshape(n_pairs, F, channels, 8)
+        return exc, movs
 
     def records(self, n_pairs, n_frames):
         """Per-frame records of the last run (needs keep_records(True))."""

@@ -111,6 +111,12 @@ static unsigned frames_for_samples(uint64_t n) {
   return (unsigned)(full + (left > 0 ? 1 : 0));
 }
 
+// 192-sample frames of the filter-bank clock: whole frames, plus one
+// zero-padded frame for the remainder (gstpeaq.c:649-652, :770-772)
+static unsigned fb_frames_for_samples(uint64_t n) {
+  return (unsigned)(n / kFbFrame + (n % kFbFrame ? 1 : 0));
+}
+
 // ---------------------------------------------------------------------------
 
 struct EventPair {
@@ -130,9 +136,23 @@ struct Engine {
   double* d_state = nullptr;
   size_t state_cap = 0;
   PairResult* d_results = nullptr;
-  unsigned long long* d_nsamples = nullptr;
-  unsigned* d_nframes = nullptr;
+  unsigned long long* d_nsamples = nullptr;       // [4][pairs_cap]: fft ref, fft test, fb ref, fb test
+  unsigned* d_nframes = nullptr;                  // [2][pairs_cap]: fft clock, fb clock
   size_t pairs_cap = 0;
+  // advanced mode workspaces
+  double* d_hp = nullptr;
+  size_t hp_cap = 0;
+  double* d_hp_state = nullptr;
+  size_t hp_state_cap = 0;
+  double* d_fbout = nullptr;
+  size_t fbout_cap = 0;
+  unsigned char* d_fbflags = nullptr;
+  size_t fbflags_cap = 0;
+  double* d_fbdbg = nullptr;
+  size_t fbdbg_cap = 0;
+  size_t last_fbdbg_doubles = 0;
+  unsigned last_fb_frames = 0;
+  size_t fb_budget_bytes = (size_t)24 << 30;
   float* d_stage[2] = {nullptr, nullptr};
   size_t stage_cap = 0;     // floats, each
   std::vector<EventPair> events;
@@ -156,6 +176,10 @@ struct Engine {
       const long mb = std::atol(env);
       if (mb > 0) record_budget_bytes = (size_t)mb << 20;
     }
+    if (const char* env = std::getenv("PEAQ_B200_FB_BUDGET_MB")) {
+      const long mb = std::atol(env);
+      if (mb > 0) fb_budget_bytes = (size_t)mb << 20;
+    }
     return 0;
   }
 
@@ -173,6 +197,11 @@ struct Engine {
     cudaFree(d_nframes);
     cudaFree(d_stage[0]);
     cudaFree(d_stage[1]);
+    cudaFree(d_hp);
+    cudaFree(d_hp_state);
+    cudaFree(d_fbout);
+    cudaFree(d_fbflags);
+    cudaFree(d_fbdbg);
     cudaFree(d_tables);
     if (stream) cudaStreamDestroy(stream);
     delete h_tables;
@@ -216,7 +245,7 @@ struct Engine {
     return 0;
   }
 
-  int ensure_pairs(size_t n_pairs, const StateLayout& S, bool preserve_state) {
+  int ensure_pairs(size_t n_pairs, size_t state_stride, bool preserve_state) {
     if (n_pairs > pairs_cap) {
       if (d_results) PEAQ_CUDA(cudaFree(d_results));
       if (d_nsamples) PEAQ_CUDA(cudaFree(d_nsamples));
@@ -225,11 +254,11 @@ struct Engine {
       d_nsamples = nullptr;
       d_nframes = nullptr;
       PEAQ_CUDA(cudaMalloc(&d_results, n_pairs * sizeof(PairResult)));
-      PEAQ_CUDA(cudaMalloc(&d_nsamples, n_pairs * sizeof(unsigned long long)));
-      PEAQ_CUDA(cudaMalloc(&d_nframes, n_pairs * sizeof(unsigned)));
+      PEAQ_CUDA(cudaMalloc(&d_nsamples, 4 * n_pairs * sizeof(unsigned long long)));
+      PEAQ_CUDA(cudaMalloc(&d_nframes, 2 * n_pairs * sizeof(unsigned)));
       pairs_cap = n_pairs;
     }
-    const size_t need = n_pairs * (size_t)S.stride;
+    const size_t need = n_pairs * state_stride;
     if (need > state_cap) {
       if (preserve_state) return fail(PEAQ_B200_ERR_INVALID, "state would be lost on growth");
       int rc = ensure(&d_state, &state_cap, need);
@@ -238,34 +267,42 @@ struct Engine {
     return 0;
   }
 
-  // Runs frames of `n_pairs` pairs whose PCM is resident on the device.
-  // h_nframes[p] frames are processed for pair p, reading from sample 0 of the
-  // given buffers.  reset_state: start from fresh state (else continue).
-  int process_resident(const float* d_ref, const float* d_test, size_t pair_stride, int n_pairs,
-                       int C, const uint64_t* h_nsamples, const unsigned* h_nframes,
-                       bool reset_state, PairResult* h_out) {
+  // Per-pair work description of one clock (host arrays, one entry per pair):
+  // signal lengths in samples per channel (zero beyond) and frames to run.
+  struct ClockPlan {
+    const uint64_t* ns_ref;
+    const uint64_t* ns_test;
+    const unsigned* nf;
+  };
+
+  int upload_plan(const ClockPlan& plan, int n_pairs, int slot) {
+    std::vector<unsigned long long> a(plan.ns_ref, plan.ns_ref + n_pairs), b(plan.ns_test, plan.ns_test + n_pairs);
+    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot) * pairs_cap, a.data(),
+                              n_pairs * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot + 1) * pairs_cap, b.data(),
+                              n_pairs * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    PEAQ_CUDA(cudaMemcpyAsync(d_nframes + (size_t)slot * pairs_cap, plan.nf, n_pairs * sizeof(unsigned),
+                              cudaMemcpyHostToDevice, stream));
+    PEAQ_CUDA(cudaStreamSynchronize(stream));   // the staging vectors die here
+    return 0;
+  }
+
+  PcmView make_view(const float* d_ref, const float* d_test, size_t pair_stride, int C, int slot) const {
+    PcmView pcm;
+    pcm.ref = d_ref;
+    pcm.test = d_test;
+    pcm.pair_stride = pair_stride;
+    pcm.n_samples = d_nsamples + (size_t)(2 * slot) * pairs_cap;
+    pcm.n_samples_test = d_nsamples + (size_t)(2 * slot + 1) * pairs_cap;
+    pcm.n_frames = d_nframes + (size_t)slot * pairs_cap;
+    pcm.channels = C;
+    return pcm;
+  }
+
+  // FFT-clock chunk loop shared by both modes: K1 then the mode's scan kernel.
+  template <typename ScanFn>
+  int run_fft_clock(const PcmView& pcm, int n_pairs, unsigned max_frames, const RecordLayout& L, ScanFn scan) {
     const int B = h_tables->fft_bands;
-    const RecordLayout L = make_record_layout(C, B);
-    const StateLayout S = make_state_layout(C, B);
-    int rc = ensure_pairs((size_t)n_pairs, S, !reset_state);
-    if (rc) return rc;
-    unsigned max_frames = 0;
-    for (int p = 0; p < n_pairs; p++) max_frames = std::max(max_frames, h_nframes[p]);
-
-    std::vector<unsigned long long> ns(h_nsamples, h_nsamples + n_pairs);
-    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples, ns.data(), n_pairs * sizeof(unsigned long long),
-                              cudaMemcpyHostToDevice, stream));
-    PEAQ_CUDA(cudaMemcpyAsync(d_nframes, h_nframes, n_pairs * sizeof(unsigned),
-                              cudaMemcpyHostToDevice, stream));
-    if (reset_state) {
-      const size_t total = (size_t)n_pairs * S.stride;
-      const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
-      init_state_kernel<<<blocks, 256, 0, stream>>>(d_state, S, n_pairs);
-      PEAQ_CUDA(cudaGetLastError());
-      launches++;
-    }
-
-    // frame chunking so that the records fit the budget
     const size_t rec_bytes = (size_t)L.stride * sizeof(double);
     size_t chunk = max_frames;
     if (chunk == 0) chunk = 1;
@@ -274,17 +311,8 @@ struct Engine {
       if (chunk < 1) chunk = 1;
     }
     if (keep_records) chunk = std::max<size_t>(max_frames, 1);
-    rc = ensure(&d_records, &records_cap, (size_t)n_pairs * chunk * L.stride);
+    int rc = ensure(&d_records, &records_cap, (size_t)n_pairs * chunk * L.stride);
     if (rc) return rc;
-
-    PcmView pcm;
-    pcm.ref = d_ref;
-    pcm.test = d_test;
-    pcm.pair_stride = pair_stride;
-    pcm.n_samples = d_nsamples;
-    pcm.n_frames = d_nframes;
-    pcm.channels = C;
-
     unsigned first = 0;
     do {
       const unsigned n = (unsigned)std::min<size_t>(chunk, max_frames - first);
@@ -295,14 +323,105 @@ struct Engine {
         if ((rc = timer_end())) return rc;
       }
       if ((rc = timer_begin(2))) return rc;
-      PEAQ_CUDA(launch_scan_basic(d_tables, d_records, L, d_nframes, first, n, d_state, S, d_results,
-                                  n_pairs, stream));
+      PEAQ_CUDA(scan(first, n));
       launches++;
       if ((rc = timer_end())) return rc;
       first += n;
     } while (first < max_frames);
     last_layout = L;
     last_records_doubles = keep_records ? (size_t)n_pairs * chunk * L.stride : 0;
+    return 0;
+  }
+
+  // Runs the frames described by the plan(s) for `n_pairs` pairs whose PCM is
+  // resident on the device, reading from sample 0 of the given buffers.
+  // reset_state: start from fresh state (else continue a session).
+  int process_resident(const float* d_ref, const float* d_test, size_t pair_stride, int n_pairs,
+                       int C, const ClockPlan& fft, const ClockPlan& fb, bool reset_state,
+                       PairResult* h_out) {
+    const int B = h_tables->fft_bands;
+    const RecordLayout L = make_record_layout(C, B);
+    const StateLayout S = make_state_layout(C, B);
+    const AdvStateLayout A = make_adv_state_layout(C);
+    int rc = ensure_pairs((size_t)n_pairs, advanced ? (size_t)A.stride : (size_t)S.stride, !reset_state);
+    if (rc) return rc;
+    unsigned max_frames = 0, max_fb_frames = 0;
+    for (int p = 0; p < n_pairs; p++) {
+      max_frames = std::max(max_frames, fft.nf[p]);
+      if (advanced) max_fb_frames = std::max(max_fb_frames, fb.nf[p]);
+    }
+    if ((rc = upload_plan(fft, n_pairs, 0))) return rc;
+    const PcmView pcm = make_view(d_ref, d_test, pair_stride, C, 0);
+
+    if (!advanced) {
+      if (reset_state) {
+        const size_t total = (size_t)n_pairs * S.stride;
+        const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+        init_state_kernel<<<blocks, 256, 0, stream>>>(d_state, S, n_pairs);
+        PEAQ_CUDA(cudaGetLastError());
+        launches++;
+      }
+      rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first, unsigned n) {
+        return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_results,
+                                 n_pairs, stream);
+      });
+      if (rc) return rc;
+    } else {
+      if (!reset_state) return fail(PEAQ_B200_ERR_INVALID, "advanced mode runs whole items");
+      if ((rc = upload_plan(fb, n_pairs, 1))) return rc;
+      const PcmView pcm_fb = make_view(d_ref, d_test, pair_stride, C, 1);
+      PEAQ_CUDA(launch_init_adv_state(d_state, A, n_pairs, stream));
+      launches++;
+      // ---- filter-bank clock: chunks of 192-sample frames -----------------------
+      const int n_streams = n_pairs * 2 * C;
+      const size_t per_frame = (size_t)n_streams * (kFbFrame * sizeof(double) + 6 * kFbBands * 2 * sizeof(double));
+      size_t chunk = std::max<unsigned>(max_fb_frames, 1);
+      if (chunk * per_frame > fb_budget_bytes) chunk = std::max<size_t>(fb_budget_bytes / per_frame, 8);
+      if (keep_records) chunk = std::max<unsigned>(max_fb_frames, 1);
+      const size_t hp_stride = kFbHist + chunk * kFbFrame;
+      if ((rc = ensure(&d_hp, &hp_cap, (size_t)n_streams * hp_stride))) return rc;
+      if ((rc = ensure(&d_hp_state, &hp_state_cap, (size_t)n_streams * 6))) return rc;
+      if ((rc = ensure(&d_fbout, &fbout_cap, (size_t)n_streams * kFbBands * chunk * 6 * 2))) return rc;
+      if ((rc = ensure(&d_fbflags, &fbflags_cap, (size_t)n_pairs * chunk))) return rc;
+      double* dbg = nullptr;
+      last_fbdbg_doubles = 0;
+      if (keep_records) {
+        const size_t need = (size_t)n_pairs * chunk * (2 * C * 2 * kFbBands + C * 8);
+        if ((rc = ensure(&d_fbdbg, &fbdbg_cap, need))) return rc;
+        PEAQ_CUDA(cudaMemsetAsync(d_fbdbg, 0, need * sizeof(double), stream));
+        dbg = d_fbdbg;
+        last_fbdbg_doubles = need;
+        last_fb_frames = (unsigned)chunk;
+      }
+      unsigned first = 0, prev_samples = 0;
+      while (first < max_fb_frames) {
+        const unsigned n = (unsigned)std::min<size_t>(chunk, max_fb_frames - first);
+        const unsigned n_sub = n * 6, samples = n * kFbFrame;
+        if ((rc = timer_begin(4))) return rc;
+        PEAQ_CUDA(launch_fb_flags(pcm_fb, n_pairs, first, n, d_fbflags, stream));
+        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples,
+                               prev_samples, d_hp, hp_stride, d_hp_state, first == 0, stream));
+        PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, stream));
+        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbout, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,
+                                 dbg, n_pairs, stream));
+        launches += 4;
+        if ((rc = timer_end())) return rc;
+        first += n;
+        prev_samples = samples;
+      }
+      if (max_fb_frames == 0) {
+        // publish the (empty) fb-clock MOVs so the epilogue sees 0/0 like the reference
+        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbout, 0, d_fbflags, pcm_fb.n_frames, 0, 0, d_state, A, nullptr,
+                                 n_pairs, stream));
+        launches++;
+      }
+      // ---- FFT clock; its epilogue combines all five MOVs ---------------------------
+      rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first_f, unsigned n) {
+        return launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, first_f, n, d_state, A, d_results,
+                                   n_pairs, stream);
+      });
+      if (rc) return rc;
+    }
 
     if (h_out) {
       PEAQ_CUDA(cudaMemcpyAsync(h_out, d_results, n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost,
@@ -322,7 +441,6 @@ static int check_channels(int channels) {
 static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out) {
   if (!e || !b || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   if (b->n_pairs <= 0) return fail(PEAQ_B200_ERR_INVALID, "n_pairs must be positive");
-  if (e->advanced) return fail(PEAQ_B200_ERR_INVALID, "advanced mode is not available in this build");
   int rc = check_channels(b->channels);
   if (rc) return rc;
   if (!b->ref || !b->test) return fail(PEAQ_B200_ERR_INVALID, "null PCM pointer");
@@ -330,13 +448,14 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
   const int C = b->channels;
   const int n_pairs = b->n_pairs;
   std::vector<uint64_t> ns(n_pairs);
-  std::vector<unsigned> nf(n_pairs);
+  std::vector<unsigned> nf(n_pairs), nfb(n_pairs);
   uint64_t max_n = 0;
   for (int p = 0; p < n_pairs; p++) {
     ns[p] = b->n_samples ? b->n_samples[p] : b->n_samples_all;
     if (ns[p] > ((uint64_t)UINT_MAX - 4) * kFftStep)
       return fail(PEAQ_B200_ERR_INVALID, "item too long");
     nf[p] = frames_for_samples(ns[p]);
+    nfb[p] = fb_frames_for_samples(ns[p]);
     max_n = std::max(max_n, ns[p]);
     if (n_pairs > 1 && ns[p] * C > b->pair_stride)
       return fail(PEAQ_B200_ERR_INVALID, "pair_stride smaller than an item");
@@ -351,7 +470,8 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
   if (b->on_device) {
     if ((reinterpret_cast<uintptr_t>(b->ref) | reinterpret_cast<uintptr_t>(b->test)) & 15)
       return fail(PEAQ_B200_ERR_INVALID, "device PCM pointers must be 16-byte aligned");
-    rc = e->process_resident(b->ref, b->test, b->pair_stride, n_pairs, C, ns.data(), nf.data(), true, res);
+    const Engine::ClockPlan fft{ns.data(), ns.data(), nf.data()}, fb{ns.data(), ns.data(), nfb.data()};
+    rc = e->process_resident(b->ref, b->test, b->pair_stride, n_pairs, C, fft, fb, true, res);
     if (rc) return rc;
   } else {
     // host input: stage sub-batches of pairs through device buffers
@@ -373,8 +493,9 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
                                   cudaMemcpyHostToDevice, e->stream));
       }
       if ((rc = e->timer_end())) return rc;
-      rc = e->process_resident(e->d_stage[0], e->d_stage[1], stride, np, C, ns.data() + p0, nf.data() + p0,
-                               true, res + p0);
+      const Engine::ClockPlan fft{ns.data() + p0, ns.data() + p0, nf.data() + p0},
+          fb{ns.data() + p0, ns.data() + p0, nfb.data() + p0};
+      rc = e->process_resident(e->d_stage[0], e->d_stage[1], stride, np, C, fft, fb, true, res + p0);
       if (rc) return rc;
     }
   }
@@ -397,10 +518,24 @@ struct Session {
   double level = 92.0;
   int channels = 0;
   Engine* engine = nullptr;
-  bool started = false;          // state initialised on the device
-  std::vector<float> fifo[2];    // GstAdapter stand-ins (ref_adapter_fft / test_adapter_fft)
+  bool started = false;          // basic mode: state initialised on the device
+  // basic mode: GstAdapter stand-ins (ref_adapter_fft / test_adapter_fft), drained as
+  // frames complete.  advanced mode: the whole item is kept (both clocks re-read it)
+  // and evaluated on demand -- see get_result / finish.
+  std::vector<float> fifo[2];
   PairResult last = {};
   bool have_result = false;
+  bool dirty = false;            // advanced: samples arrived since `last` was computed
+  bool flushed = false;          // advanced: finish() seen (one padded frame per clock)
+
+  void reset_stream() {
+    started = false;
+    have_result = false;
+    dirty = false;
+    flushed = false;
+    fifo[0].clear();
+    fifo[1].clear();
+  }
 
   void drop_engine() {
     if (engine) {
@@ -408,10 +543,7 @@ struct Session {
       delete engine;
       engine = nullptr;
     }
-    started = false;
-    have_result = false;
-    fifo[0].clear();
-    fifo[1].clear();
+    reset_stream();
   }
 
   int ensure_engine() {
@@ -430,24 +562,32 @@ struct Session {
     return rc;
   }
 
-  // run `k` frames whose samples are the first (k-1)*1024+2048 of both FIFOs,
-  // or (padded != nullptr) one explicit zero-padded frame pair
-  int run_frames(unsigned k, const float* ref, const float* test, size_t n_samples) {
-    int rc = ensure_engine();
-    if (rc) return rc;
-    if (engine->advanced) return fail(PEAQ_B200_ERR_INVALID, "advanced mode is not available in this build");
-    PEAQ_CUDA(cudaSetDevice(device));
-    const size_t floats = n_samples * channels;
+  int stage(const float* ref, size_t ref_floats, const float* test, size_t test_floats) {
+    const size_t floats = std::max(ref_floats, test_floats);
     size_t cap0 = engine->stage_cap, cap1 = engine->stage_cap;
+    int rc;
     if ((rc = engine->ensure(&engine->d_stage[0], &cap0, std::max<size_t>(floats, 4)))) return rc;
     if ((rc = engine->ensure(&engine->d_stage[1], &cap1, std::max<size_t>(floats, 4)))) return rc;
     engine->stage_cap = std::min(cap0, cap1);
-    PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0], ref, floats * sizeof(float), cudaMemcpyHostToDevice,
-                              engine->stream));
-    PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[1], test, floats * sizeof(float), cudaMemcpyHostToDevice,
-                              engine->stream));
+    if (ref_floats)
+      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0], ref, ref_floats * sizeof(float), cudaMemcpyHostToDevice,
+                                engine->stream));
+    if (test_floats)
+      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[1], test, test_floats * sizeof(float), cudaMemcpyHostToDevice,
+                                engine->stream));
+    return 0;
+  }
+
+  // basic mode: run `k` frames over the first n_samples samples of both buffers
+  int run_frames(unsigned k, const float* ref, const float* test, size_t n_samples) {
+    int rc = ensure_engine();
+    if (rc) return rc;
+    PEAQ_CUDA(cudaSetDevice(device));
+    const size_t floats = n_samples * channels;
+    if ((rc = stage(ref, floats, test, floats))) return rc;
     const uint64_t ns = n_samples;
-    rc = engine->process_resident(engine->d_stage[0], engine->d_stage[1], floats, 1, channels, &ns, &k,
+    const Engine::ClockPlan plan{&ns, &ns, &k};
+    rc = engine->process_resident(engine->d_stage[0], engine->d_stage[1], floats, 1, channels, plan, plan,
                                   !started, &last);
     if (rc) return rc;
     started = true;
@@ -455,7 +595,7 @@ struct Session {
     return 0;
   }
 
-  // do_processing (gstpeaq.c:596-611)
+  // do_processing (gstpeaq.c:596-611), basic mode
   int drain() {
     const size_t fl = std::min(fifo[0].size(), fifo[1].size());
     const size_t frame = (size_t)kFftFrame * channels, step = (size_t)kFftStep * channels;
@@ -465,6 +605,46 @@ struct Session {
     int rc = run_frames(k, fifo[0].data(), fifo[1].data(), n_samples);
     if (rc) return rc;
     for (int s = 0; s < 2; s++) fifo[s].erase(fifo[s].begin(), fifo[s].begin() + (size_t)k * step);
+    return 0;
+  }
+
+  // What one clock (frame size F, step St) has processed of streams of nr / nt
+  // samples: do_processing runs while BOTH hold a frame; do_flush (if `flush`)
+  // adds one zero-padded frame made of MIN(left, F) samples of each stream.
+  static void clock_plan(uint64_t nr, uint64_t nt, unsigned F, unsigned St, bool flush, uint64_t* er,
+                         uint64_t* et, unsigned* frames) {
+    const uint64_t m = std::min(nr, nt);
+    const uint64_t k = m >= F ? (m - F) / St + 1 : 0;
+    uint64_t lr = nr - k * St, lt = nt - k * St;   // left in the adapters
+    unsigned f = (unsigned)k;
+    uint64_t use_r = k ? (k - 1) * St + F : 0, use_t = use_r;
+    if (flush && (lr || lt)) {
+      use_r = k * St + std::min<uint64_t>(lr, F);
+      use_t = k * St + std::min<uint64_t>(lt, F);
+      f += 1;
+    }
+    *er = std::min(use_r, nr);
+    *et = std::min(use_t, nt);
+    *frames = f;
+  }
+
+  // advanced mode: evaluate everything received so far
+  int evaluate_advanced() {
+    int rc = ensure_engine();
+    if (rc) return rc;
+    PEAQ_CUDA(cudaSetDevice(device));
+    const uint64_t nr = fifo[0].size() / channels, nt = fifo[1].size() / channels;
+    uint64_t fr, ft, br, bt;
+    unsigned ff, fbf;
+    clock_plan(nr, nt, kFftFrame, kFftStep, flushed, &fr, &ft, &ff);
+    clock_plan(nr, nt, kFbFrame, kFbFrame, flushed, &br, &bt, &fbf);
+    if ((rc = stage(fifo[0].data(), fifo[0].size(), fifo[1].data(), fifo[1].size()))) return rc;
+    const Engine::ClockPlan fft{&fr, &ft, &ff}, fb{&br, &bt, &fbf};
+    rc = engine->process_resident(engine->d_stage[0], engine->d_stage[1],
+                                  std::max(fifo[0].size(), fifo[1].size()), 1, channels, fft, fb, true, &last);
+    if (rc) return rc;
+    have_result = true;
+    dirty = false;
     return 0;
   }
 };
@@ -620,6 +800,18 @@ int peaq_b200_engine_copy_records(peaq_b200_engine* h, double* dst, size_t max_d
   return 0;
 }
 
+int peaq_b200_engine_copy_fb_debug(peaq_b200_engine* h, double* dst, size_t max_doubles, size_t* n_doubles,
+                                   uint32_t* frames) {
+  if (!h || !dst) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  const size_t n = std::min(max_doubles, e->last_fbdbg_doubles);
+  PEAQ_CUDA(cudaSetDevice(e->device));
+  if (n) PEAQ_CUDA(cudaMemcpy(dst, e->d_fbdbg, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_doubles) *n_doubles = n;
+  if (frames) *frames = e->last_fb_frames;
+  return 0;
+}
+
 int peaq_b200_table(int advanced, double playback_level, int model, int which, double* out) {
   if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   DeviceTables* tp = new (std::nothrow) DeviceTables;
@@ -707,10 +899,7 @@ int peaq_b200_session_set_channels(peaq_b200_session* h, int channels) {
   if (rc) return rc;
   Session* s = reinterpret_cast<Session*>(h);
   // set_caps frees and reallocates all per-channel state (gstpeaq.c:575-586)
-  s->started = false;
-  s->have_result = false;
-  s->fifo[0].clear();
-  s->fifo[1].clear();
+  s->reset_stream();
   s->channels = channels;
   return 0;
 }
@@ -721,6 +910,10 @@ int peaq_b200_session_push(peaq_b200_session* h, int pad, const float* data, siz
   Session* s = reinterpret_cast<Session*>(h);
   if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
   s->fifo[pad].insert(s->fifo[pad].end(), data, data + n * s->channels);
+  if (s->advanced) {
+    s->dirty = true;   // evaluated lazily: both clocks re-read the whole item
+    return 0;
+  }
   return s->drain();
 }
 
@@ -728,6 +921,10 @@ int peaq_b200_session_finish(peaq_b200_session* h) {
   if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   Session* s = reinterpret_cast<Session*>(h);
   if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
+  if (s->advanced) {
+    s->flushed = true;
+    return s->evaluate_advanced();
+  }
   int rc = s->drain();
   if (rc) return rc;
   // do_flush (gstpeaq.c:716-745): one zero-padded frame from whatever is left
@@ -748,6 +945,10 @@ int peaq_b200_session_finish(peaq_b200_session* h) {
 int peaq_b200_session_get_result(peaq_b200_session* h, peaq_b200_result* out) {
   if (!h || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   Session* s = reinterpret_cast<Session*>(h);
+  if (s->advanced && s->dirty && s->channels) {
+    int rc = s->evaluate_advanced();
+    if (rc) return rc;
+  }
   if (!s->have_result) {
     // no frame processed yet: the reference would evaluate empty accumulators
     // (0/0); report that state without touching the GPU

@@ -70,6 +70,37 @@ inline StateLayout make_state_layout(int C, int B) {
   return S;
 }
 
+// Per-pair recurrent state, advanced mode (doubles unless noted).
+struct AdvStateLayout {
+  int C;
+  int off_fft_filtered;   // [c][55]            time smearing of the ref excitation
+  int off_fft_acc;        // [c][2][kAccFields] SegmentalNMR, EHS
+  int off_fft_scalar;     // signal / noise energy
+  int off_fb_stream;      // [2C streams][cu 40 | excitation 40 | history 11 x 40]
+  int off_fb_level;       // [c][6][40]
+  int off_fb_mod;         // [c][ref|test][3][40]
+  int off_fb_acc;         // [c][3][kAccFields] RmsModDiff, RmsNoiseLoudAsym, AvgLinDist
+  int off_fb_movs;        // 3 channel-averaged MOV values published by the fb scan
+  int off_ints;           // int32: fft status, fft frames, fb status, fb frames, loudness frame, history slot
+  int stride;
+};
+
+inline AdvStateLayout make_adv_state_layout(int C) {
+  AdvStateLayout S;
+  S.C = C;
+  S.off_fft_filtered = 0;
+  S.off_fft_acc = C * 55;
+  S.off_fft_scalar = S.off_fft_acc + C * 2 * kAccFields;
+  S.off_fb_stream = S.off_fft_scalar + 2;
+  S.off_fb_level = S.off_fb_stream + 2 * C * 13 * kFbBands;
+  S.off_fb_mod = S.off_fb_level + C * 6 * kFbBands;
+  S.off_fb_acc = S.off_fb_mod + C * 2 * 3 * kFbBands;
+  S.off_fb_movs = S.off_fb_acc + C * 3 * kAccFields;
+  S.off_ints = S.off_fb_movs + 3;
+  S.stride = S.off_ints + 4;
+  return S;
+}
+
 // Mirrors peaq_b200_result of the C ABI (include/peaq_b200.h).
 struct PairResult {
   double odg;
@@ -88,8 +119,9 @@ struct PcmView {
   const float* ref;
   const float* test;
   size_t pair_stride;
-  const unsigned long long* n_samples;  // device, per pair
-  const unsigned* n_frames;             // device, per pair: FFT-clock frames to run
+  const unsigned long long* n_samples;       // device, per pair: length of the ref signal
+  const unsigned long long* n_samples_test;  // device, per pair: length of the test signal
+  const unsigned* n_frames;                  // device, per pair: frames of this clock to run
   int channels;
 };
 
@@ -114,5 +146,25 @@ cudaError_t launch_scan_basic(const DeviceTables* d_tables, const double* record
                               PairResult* results, int n_pairs, cudaStream_t stream);
 
 size_t fft_frames_smem_bytes(int channels);
+
+// advanced mode (peaq_fb.cu, peaq_scan_adv.cu)
+cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsigned n_chunk_frames,
+                            unsigned char* flags, cudaStream_t stream);
+cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
+                         unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                         double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
+                         cudaStream_t stream);
+cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
+                           const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
+                           double* fbout, cudaStream_t stream);
+cudaError_t launch_init_adv_state(double* state, AdvStateLayout S, int n_pairs, cudaStream_t stream);
+cudaError_t launch_fb_scan(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
+                           const unsigned char* flags, const unsigned* n_frames, unsigned first_frame,
+                           unsigned n_chunk_frames, double* state, AdvStateLayout S, double* dbg,
+                           int n_pairs, cudaStream_t stream);
+cudaError_t launch_adv_fft_scan(const DeviceTables* d_tables, const double* records, RecordLayout L,
+                                const unsigned* n_frames, unsigned first_frame, unsigned n_chunk_frames,
+                                double* state, AdvStateLayout S, PairResult* results, int n_pairs,
+                                cudaStream_t stream);
 
 }  // namespace peaq

@@ -1,0 +1,268 @@
+// Filter-bank ear model of advanced-mode PEAQ (fbearmodel.c), front half:
+//
+//   FB0 fb_flags_kernel   above-threshold flag of every 192-sample frame
+//                         (is_frame_above_threshold, gstpeaq.c:1081-1099, called
+//                         from process_fb_block :970-971)
+//   FB1 fb_hp_kernel      playback-level scaling + DC-reject filter, two cascaded
+//                         biquads (fbearmodel.c:289-303): sequential in time, one
+//                         thread per stream, state carried between chunks
+//   FB2 fb_bank_kernel    40 complex FIR filters of 52..1456 taps evaluated every
+//                         32 samples (apply_filter_bank, fbearmodel.c:398-435)
+//
+// FB2 is the contraction-shaped stage (2.8 M FMA per stereo PEAQ frame).  It is
+// computed as 32 polyphase sub-convolutions: with delay d = 32 q + j,
+//   out_b[s] = sum_j sum_q G_b[32 q + j] * x[32 (s - q) - j]
+// so for a fixed phase j consecutive outputs slide over the same decimated
+// input sequence.  Each lane owns R = 7 consecutive outputs and keeps the sliding
+// window in registers: one shared-memory load and one coefficient load feed 14
+// FMAs.  The input tile is staged in shared memory in polyphase-transposed layout
+// (row stride 273 doubles: conflict-free for the transposing store and for the
+// stride-7 window loads).
+//
+// Coefficients G_b[d] are indexed by total delay d (band delay D = 1 + (1456-N)/2
+// folded in, fbearmodel.c:408), full length (the reference exploits the
+// even/odd symmetry, :418-425; same products, different summation order), and
+// reproduce the reference's ring-buffer alias: for band 0 the tap at delay 1456
+// reads the NEWEST sample (fb_buf[offset + 1456] == fb_buf[offset]).
+#include "peaq_engine.h"
+
+namespace peaq {
+namespace {
+
+constexpr int kR = 7;                    // outputs per lane
+constexpr int kTileOut = 32 * kR;        // sub-steps per tile (224)
+constexpr int kMaxQ = 46;                // ceil(1457 / 32)
+constexpr int kTileM = kTileOut + kMaxQ + 1;   // decimated samples per phase (271)
+constexpr int kRowStride = 273;
+constexpr int kBankWarps = 8;
+
+// ---------------------------------------------------------------------------
+
+__global__ void fb_flags_kernel(PcmView pcm, unsigned first_frame, unsigned n_chunk_frames,
+                                unsigned char* __restrict__ flags) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pair = blockIdx.y;
+  if (idx >= n_chunk_frames) return;
+  const unsigned frame = first_frame + idx;
+  unsigned char above = 0;
+  if (frame < pcm.n_frames[pair]) {
+    const int C = pcm.channels;
+    const unsigned long long n = pcm.n_samples[pair];
+    const float* __restrict__ sig = pcm.ref + (size_t)pair * pcm.pair_stride;
+    const unsigned long long s0 = (unsigned long long)frame * kFbFrame;
+    for (int c = 0; c < C && !above; c++) {
+      // literal replay: float running sum, double increments (gstpeaq.c:1088-1096)
+      float sum = 0;
+      double hist[5];
+      int i;
+      for (i = 0; i < 5; i++) {
+        const unsigned long long s = s0 + i;
+        hist[i] = fabs((double)(s < n ? __ldg(sig + s * C + c) : 0.f));
+        sum = (float)((double)sum + hist[i]);
+      }
+      for (; i < kFbFrame; i++) {
+        const unsigned long long s = s0 + i;
+        const double v = fabs((double)(s < n ? __ldg(sig + s * C + c) : 0.f));
+        sum = (float)((double)sum + (v - hist[i % 5]));
+        hist[i % 5] = v;
+        if ((double)sum >= 200. / 32768) {
+          above = 1;
+          break;
+        }
+      }
+    }
+  }
+  flags[(size_t)pair * n_chunk_frames + idx] = above;
+}
+
+// ---------------------------------------------------------------------------
+// FB1.  hp buffer per stream: [kFbHist history samples][chunk samples].
+
+__global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams,
+                             unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                             double* __restrict__ hp, size_t hp_stride,
+                             double* __restrict__ hp_state /* [stream][6] */, int first_chunk) {
+  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stream >= n_streams) return;
+  const int C = pcm.channels;
+  const int pair = stream / (2 * C);
+  const int rem = stream - pair * 2 * C;
+  const int chan = rem >> 1, side = rem & 1;
+  const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
+  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
+  double* __restrict__ out = hp + (size_t)stream * hp_stride;
+  double* st = hp_state + (size_t)stream * 6;
+  // history for the FIR bank: last kFbHist samples of the previous chunk
+  if (first_chunk) {
+    for (int i = 0; i < kFbHist; i++) out[i] = 0.;
+  } else {
+    for (int i = 0; i < kFbHist; i++) out[i] = out[prev_chunk_samples + i];
+  }
+  double x1 = 0, x2 = 0, y1a = 0, y2a = 0, y1b = 0, y2b = 0;
+  if (!first_chunk) {
+    x1 = st[0]; x2 = st[1]; y1a = st[2]; y2a = st[3]; y1b = st[4]; y2b = st[5];
+  }
+  const double lf = T->level_factor_fb;
+  // the item may end inside the chunk: samples past the end are zero (do_flush
+  // pads the last frame, gstpeaq.c:731-736); frames past the padded one are never read
+  for (unsigned i = 0; i < chunk_samples; i++) {
+    const unsigned long long s = t0 + i;
+    const float x = s < n ? __ldg(sig + s * C + chan) : 0.f;
+    const double scaled = x * lf;
+    const double h1 = scaled - 2. * x1 + x2 + 1.99517 * y1a - 0.995174 * y2a;
+    const double h2 = h1 - 2. * y1a + y2a + 1.99799 * y1b - 0.997998 * y2b;
+    x2 = x1;
+    x1 = scaled;
+    y2a = y1a;
+    y1a = h1;
+    y2b = y1b;
+    y1b = h2;
+    out[kFbHist + i] = h2;
+  }
+  st[0] = x1; st[1] = x2; st[2] = y1a; st[3] = y2a; st[4] = y1b; st[5] = y2b;
+}
+
+// ---------------------------------------------------------------------------
+// FB2
+
+struct BankBands {
+  // bands handled by each of the kBankWarps warps (balanced by filter length)
+  signed char band[kBankWarps][8];
+};
+
+__global__ void __launch_bounds__(32 * kBankWarps)
+fb_bank_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp, size_t hp_stride,
+               unsigned n_sub /* sub-steps in this chunk */, double2* __restrict__ fbout,
+               size_t out_stream_stride /* = 40 * n_sub */, BankBands bands, int n_tiles) {
+  extern __shared__ __align__(16) double xs[];   // [32][kRowStride]
+  const int stream = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x - stream * n_tiles;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S0 = tile * kTileOut;          // first sub-step of the tile (chunk-local)
+  // decimated index m (chunk-local, x[32 m + p] = hpbuf[kFbHist + 32 m + p]); tile needs
+  // m in [S0 - kMaxQ - 1, S0 + kTileOut)
+  const int mbase = S0 - kMaxQ - 1;
+  const double* __restrict__ src = hp + (size_t)stream * hp_stride + kFbHist;
+  for (int i = threadIdx.x; i < kTileM * 32; i += blockDim.x) {
+    const int t = mbase * 32 + i;          // chunk-local sample index (>= -kFbHist)
+    const int p = i & 31, mm = i >> 5;
+    const bool ok = t < (int)(n_sub * 32) && t >= -kFbHist;
+    xs[p * kRowStride + mm] = ok ? src[t] : 0.;
+  }
+  __syncthreads();
+
+  const int s0 = S0 + kR * lane;           // this lane's first output
+  for (int slot = 0; slot < 8; slot++) {
+    const int b = bands.band[warp][slot];
+    if (b < 0) break;
+    const int dlo = T->fb_dlo[b], dhi = T->fb_dhi[b];
+    const double2* __restrict__ G = reinterpret_cast<const double2*>(T->fb_g) + T->fb_g_offset[b];
+    double are[kR], aim[kR];
+#pragma unroll
+    for (int r = 0; r < kR; r++) are[r] = aim[r] = 0.;
+    for (int j = 0; j < 32; j++) {
+      // taps d = 32 q + j within [dlo, dhi]
+      const int qlo = dlo > j ? (dlo - j + 31) >> 5 : 0;
+      const int qhi = dhi >= j ? (dhi - j) >> 5 : -1;
+      const int qn = qhi - qlo + 1;
+      if (qn <= 0) continue;
+      // x[32 (s - q) - j] = xs[p][s - q - moff - mbase]
+      const int p = (32 - j) & 31, moff = j > 0 ? 1 : 0;
+      const double* __restrict__ row = xs + p * kRowStride + (s0 - qlo - moff - mbase);
+      // coefficients of this phase are contiguous: Gp[j][q]
+      const double2* __restrict__ g = G + T->fb_phase_offset[b * 32 + j];
+      double w[kR];
+#pragma unroll
+      for (int r = 0; r < kR; r++) w[r] = row[r];
+      for (int u0 = 0; u0 < qn; u0 += kR) {
+#pragma unroll
+        for (int u = 0; u < kR; u++) {
+          if (u0 + u < qn) {
+            const double2 c = __ldg(g + u0 + u);
+#pragma unroll
+            for (int r = 0; r < kR; r++) {
+              const double x = w[(r - u + kR) % kR];
+              are[r] = fma(x, c.x, are[r]);
+              aim[r] = fma(x, c.y, aim[r]);
+            }
+            // slide: the slot of output kR-1 is free, it becomes output 0 of tap q+1
+            w[(kR - 1 - u) % kR] = row[-(u0 + u) - 1];
+          }
+        }
+      }
+    }
+    // band-major output [stream][band][sub-step]: 7 consecutive sub-steps per lane
+    double2* __restrict__ o = fbout + (size_t)stream * out_stream_stride + (size_t)b * n_sub;
+#pragma unroll
+    for (int r = 0; r < kR; r++)
+      if (s0 + r < (int)n_sub) o[s0 + r] = make_double2(are[r], aim[r]);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsigned n_chunk_frames,
+                            unsigned char* flags, cudaStream_t stream) {
+  if (n_pairs <= 0 || n_chunk_frames == 0) return cudaSuccess;
+  for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+    const int np = n_pairs - p0 < 65535 ? n_pairs - p0 : 65535;
+    PcmView v = pcm;
+    v.ref += (size_t)p0 * pcm.pair_stride;
+    v.test += (size_t)p0 * pcm.pair_stride;
+    v.n_samples += p0;
+    v.n_samples_test += p0;
+    v.n_frames += p0;
+    dim3 grid((n_chunk_frames + 127) / 128, np);
+    fb_flags_kernel<<<grid, 128, 0, stream>>>(v, first_frame, n_chunk_frames,
+                                              flags + (size_t)p0 * n_chunk_frames);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
+                         unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                         double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
+                         cudaStream_t stream) {
+  const int n_streams = n_pairs * 2 * pcm.channels;
+  if (n_streams <= 0) return cudaSuccess;
+  // few threads per block so the streams spread over all SMs (latency-bound scan)
+  const int block = 32;
+  fb_hp_kernel<<<(n_streams + block - 1) / block, block, 0, stream>>>(
+      d_tables, pcm, n_streams, t0, chunk_samples, prev_chunk_samples, hp, hp_stride, hp_state,
+      first_chunk ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
+                           const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
+                           double* fbout, cudaStream_t stream) {
+  if (n_streams <= 0 || n_sub == 0) return cudaSuccess;
+  // distribute the 40 bands over the warps, longest filters first, always onto
+  // the least loaded warp
+  BankBands bb;
+  int load[kBankWarps] = {0};
+  int count[kBankWarps] = {0};
+  for (int w = 0; w < kBankWarps; w++)
+    for (int s = 0; s < 8; s++) bb.band[w][s] = -1;
+  for (int b = 0; b < kFbBands; b++) {   // lengths are sorted descending already
+    int best = 0;
+    for (int w = 1; w < kBankWarps; w++)
+      if (load[w] < load[best]) best = w;
+    bb.band[best][count[best]++] = (signed char)b;
+    load[best] += h_tables->fb_len[b] + 64;
+  }
+  const size_t smem = sizeof(double) * 32 * kRowStride;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fb_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_tiles = (int)((n_sub + kTileOut - 1) / kTileOut);
+  fb_bank_kernel<<<(unsigned)n_streams * n_tiles, 32 * kBankWarps, smem, stream>>>(
+      d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, bb,
+      n_tiles);
+  return cudaGetLastError();
+}
+
+}  // namespace peaq

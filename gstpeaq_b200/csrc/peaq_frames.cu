@@ -297,7 +297,8 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   for (int i = threadIdx.x; i < 768; i += blockDim.x)
     tw[i] = make_double2(T->tw1024[i].x, T->tw1024[i].y);
 
-  const unsigned long long n_samples = pcm.n_samples[pair];
+  const unsigned long long n_ref = pcm.n_samples[pair], n_test = pcm.n_samples_test[pair];
+  const unsigned long long n_samples = side ? n_test : n_ref;
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
   const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
 
@@ -326,7 +327,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     const float* __restrict__ ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
     double es = 0., en = 0.;
     for (int i = lane; i < kFftFrame / 2; i += 32) {
-      const float r = pcm_at(ref_sig, s0, n_samples, i, chan, C);
+      const float r = pcm_at(ref_sig, s0, n_ref, i, chan, C);
       const float t = pcm_at(sig, s0, n_samples, i, chan, C);
       es += (double)(r * r);
       en += (double)((r - t) * (r - t));

@@ -1,0 +1,626 @@
+// Advanced-mode recurrent kernels.
+//
+// FB3 `fb_scan_kernel`: back half of the filter-bank ear model and everything
+// that runs on the 192-sample clock.  One CTA per pair, one warp per stream
+// (channel, ref|test), lane = band (40 bands: lane l owns band l and, for l < 8,
+// band 32 + l).  Per 32-sample sub-step (fbearmodel.c:320-369): level dependent
+// slope with its first-order smoothing `cu`, upward spreading as 39 lock-step
+// shared-memory steps, downward spreading, rectification, 11-deep history.  Per
+// frame (6 sub-steps): backward-masking FIR, internal noise, forward masking
+// (fbearmodel.c:371-395); then per channel (the ref warp): level / pattern
+// adaptation and modulation at 40 bands (leveladapter.c, modpatt.c), loudness
+// latch, RmsModDiffA, RmsNoiseLoudAsymA, AvgLinDistA with their accumulators
+// (process_fb_block, gstpeaq.c:965-1010; movs.c:205-254, 551-577, 679-743).
+//
+// `adv_fft_scan_kernel`: the 1024-sample clock of advanced mode
+// (process_fft_block_advanced, gstpeaq.c:924-962): time smearing of the ref
+// excitation at 55 bands, SegmentalNMRB, EHSB, SNR sums; its epilogue combines
+// all five MOVs through the 5-5-1 network (nn.c:304-335, 372-375).
+//
+// Compiled with -fmad=false (reference rounding); recurrent state is loaded
+// from / stored to global memory at chunk boundaries.
+#include "peaq_engine.h"
+
+#include <climits>
+
+namespace peaq {
+namespace {
+
+constexpr double kSlopeA = 0.993355506255034;   // fbearmodel.c:49
+constexpr double kDist = 0.921851456499719;     // fbearmodel.c:50
+constexpr double kCl = 0.0802581846102741;      // fbearmodel.c:51
+enum { kStInit = 0, kStNormal = 1, kStTentative = 2 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// calc_noise_loudness band term (movs.c:725-738)
+__device__ __forceinline__ double nl_term(double alpha, double thres_fac, double S0, double ethres,
+                                          double ref_mod, double test_mod, double ep_ref,
+                                          double ep_test) {
+  const double sref = thres_fac * ref_mod + S0;
+  const double stest = thres_fac * test_mod + S0;
+  const double beta = exp(-alpha * (ep_test - ep_ref) / ep_ref);
+  const double d = stest * ep_test - sref * ep_ref;
+  return pow(ethres / stest, 0.23) * (pow(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta), 0.23) - 1.);
+}
+
+struct FbSmem {
+  double a_re[2 * kMaxChannels][kFbBands];
+  double a_im[2 * kMaxChannels][kFbBands];
+  double hist[2 * kMaxChannels][11][kFbBands];
+  double ex_u[2 * kMaxChannels][kFbBands];
+  double ex_e[2 * kMaxChannels][kFbBands];
+  double pa[kMaxChannels][2][kFbBands];
+  double acc[kMaxChannels][3][kAccFields];
+  int latch;
+};
+
+__global__ void __launch_bounds__(64 * kMaxChannels)
+fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ fbout,
+               unsigned n_sub /* sub-steps per stream in this chunk */,
+               const unsigned char* __restrict__ flags, const unsigned* __restrict__ n_frames,
+               unsigned first_frame, unsigned n_chunk_frames, double* __restrict__ state,
+               AdvStateLayout S, double* __restrict__ dbg) {
+  __shared__ FbSmem sm;
+  const int C = S.C;
+  const int pair = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chan = warp >> 1, side = warp & 1;
+  const int stream = pair * 2 * C + warp;
+  double* st = state + (size_t)pair * S.stride;
+  int* st_ints = reinterpret_cast<int*>(st + S.off_ints);
+
+  // ---- load state -----------------------------------------------------------
+  double cu[2], exc[2];
+  double lv[6][2];       // ref_filt, test_filt, num, den, pc_ref, pc_test (channel warps)
+  double md[2][3][2];    // [ref|test][prev, filt_loud, filt_deriv][slot]      (channel warps)
+  double* st_stream = st + S.off_fb_stream + warp * (2 + 11) * kFbBands;
+#pragma unroll
+  for (int sl = 0; sl < 2; sl++) {
+    const int b = lane + 32 * sl;
+    const bool ok = b < kFbBands;
+    cu[sl] = ok ? st_stream[b] : 0.;
+    exc[sl] = ok ? st_stream[kFbBands + b] : 0.;
+    for (int i = 0; i < 11; i++)
+      if (ok) sm.hist[warp][i][b] = st_stream[(2 + i) * kFbBands + b];
+    for (int f = 0; f < 6; f++)
+      lv[f][sl] = (ok && side == 0) ? st[S.off_fb_level + (chan * 6 + f) * kFbBands + b] : 0.;
+    for (int sd = 0; sd < 2; sd++)
+      for (int f = 0; f < 3; f++)
+        md[sd][f][sl] = (ok && side == 0) ? st[S.off_fb_mod + ((chan * 2 + sd) * 3 + f) * kFbBands + b] : 0.;
+  }
+  if (side == 0 && lane < 3 * kAccFields)
+    sm.acc[chan][lane / kAccFields][lane % kAccFields] = st[S.off_fb_acc + chan * 3 * kAccFields + lane];
+  int status = st_ints[2];
+  unsigned frame_counter = (unsigned)st_ints[3];
+  unsigned loud_frame = (unsigned)st_ints[4];
+  int pos = st_ints[5];          // slot of the newest history entry
+  __syncthreads();
+
+  double fc[2], in_noise[2], in03[2], a_ear[2], a_proc[2], ethres[2], thres[2], loudfac[2];
+#pragma unroll
+  for (int sl = 0; sl < 2; sl++) {
+    const int b = min(lane + 32 * sl, kFbBands - 1);
+    fc[sl] = T->fb.fc[b];
+    in_noise[sl] = T->fb.internal_noise[b];
+    in03[sl] = T->fb.internal_noise_pow03[b];
+    a_ear[sl] = T->fb.a_ear[b];
+    a_proc[sl] = T->fb.a_proc[b];
+    ethres[sl] = T->fb.ethres[b];
+    thres[sl] = T->fb.thres[b];
+    loudfac[sl] = T->fb.loudfac[b];
+  }
+  const double deriv_factor = (double)48000 / kFbFrame;
+  const double2* __restrict__ my_out = fbout + (size_t)stream * kFbBands * n_sub;
+
+  const unsigned total = n_frames[pair];
+  const unsigned end = min(first_frame + n_chunk_frames, total);
+  for (unsigned f = first_frame; f < end; f++) {
+    const unsigned fl = f - first_frame;
+    const bool above = flags[(size_t)pair * n_chunk_frames + fl] != 0;
+    if (threadIdx.x == 0) sm.latch = 0;   // set after the first barrier, read after the second
+    // ---- six sub-steps of the ear model (fbearmodel.c:314-369) ----------------
+    for (int sub = 0; sub < 6; sub++) {
+      const unsigned s = fl * 6 + sub;
+      double d1[2], d2[2];
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        if (b < kFbBands) {
+          const double2 o = my_out[(size_t)b * n_sub + s];
+          const double L = 10 * log10(o.x * o.x + o.y * o.y);
+          const double slope = 24 + 230 / fc[sl] - 0.2 * L;
+          const double sl_eff = 4 > slope ? 4 : slope;      // MAX (4, ...), fbearmodel.c:329
+          const double dist_s = pow(kDist, sl_eff);
+          cu[sl] = cu[sl] + kSlopeA * (dist_s - cu[sl]);
+          d1[sl] = o.x;
+          d2[sl] = o.y;
+          sm.a_re[warp][b] = o.x;
+          sm.a_im[warp][b] = o.y;
+        }
+      }
+      __syncwarp();
+      // upward spreading: source band b adds out[b] * cu[b]^k to band b + k
+      for (int k = 1; k < kFbBands; k++) {
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+          const int b = lane + 32 * sl;
+          if (b + k < kFbBands) {
+            d1[sl] *= cu[sl];
+            d2[sl] *= cu[sl];
+            sm.a_re[warp][b + k] += d1[sl];
+            sm.a_im[warp][b + k] += d2[sl];
+          }
+        }
+        __syncwarp();
+      }
+      // downward spreading with the constant slope CL (fbearmodel.c:351-354)
+      if (lane == 0) {
+        double re = sm.a_re[warp][kFbBands - 1], im = sm.a_im[warp][kFbBands - 1];
+        for (int band = kFbBands - 1; band > 0; band--) {
+          re = sm.a_re[warp][band - 1] + kCl * re;
+          im = sm.a_im[warp][band - 1] + kCl * im;
+          sm.a_re[warp][band - 1] = re;
+          sm.a_im[warp][band - 1] = im;
+        }
+      }
+      __syncwarp();
+      // rectification + history (fbearmodel.c:357-368)
+      pos = pos == 10 ? 0 : pos + 1;
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        if (b < kFbBands) {
+          const double re = sm.a_re[warp][b], im = sm.a_im[warp][b];
+          sm.hist[warp][pos][b] = re * re + im * im;
+        }
+      }
+      __syncwarp();
+    }
+    // ---- backward masking, noise, forward masking (fbearmodel.c:371-395) -------
+    double U[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++) {
+      const int b = lane + 32 * sl;
+      U[sl] = 0.;
+      if (b < kFbBands) {
+        double e1 = 0.;
+        for (int i = 0; i < 5; i++) {
+          const int pa_ = pos - i < 0 ? pos - i + 11 : pos - i;
+          const int pb_ = pos - (10 - i) < 0 ? pos - (10 - i) + 11 : pos - (10 - i);
+          e1 += (sm.hist[warp][pa_][b] + sm.hist[warp][pb_][b]) * T->fb_back_mask[i];
+        }
+        {
+          const int pc_ = pos - 5 < 0 ? pos - 5 + 11 : pos - 5;
+          e1 += sm.hist[warp][pc_][b] * T->fb_back_mask[5];
+        }
+        U[sl] = e1 + in_noise[sl];
+        exc[sl] = a_ear[sl] * exc[sl] + (1. - a_ear[sl]) * U[sl];
+        sm.ex_u[warp][b] = U[sl];
+        sm.ex_e[warp][b] = exc[sl];
+      }
+    }
+    if (dbg) {
+      // [pair][frame][stream][U|E][40]
+      double* d = dbg + (((size_t)pair * n_chunk_frames + fl) * 2 * C + warp) * 2 * kFbBands;
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        if (b < kFbBands) {
+          d[b] = U[sl];
+          d[kFbBands + b] = exc[sl];
+        }
+      }
+    }
+    __syncthreads();   // excitations of all streams visible
+
+    // ---- channel processing on the ref warp (apply_ear_model_and_preprocess) ----
+    double adr[2], adt[2], mod_r[2], mod_t[2], avl_r[2], Er[2];
+    if (side == 0) {
+      double Et[2], Ur[2], Ut[2], lcr[2], lct[2];
+      double p_num = 0., p_den = 0., l_r = 0., l_t = 0.;
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        const bool ok = b < kFbBands;
+        const int bb = ok ? b : 0;
+        Er[sl] = sm.ex_e[2 * chan][bb];
+        Et[sl] = sm.ex_e[2 * chan + 1][bb];
+        Ur[sl] = sm.ex_u[2 * chan][bb];
+        Ut[sl] = sm.ex_u[2 * chan + 1][bb];
+        // leveladapter.c:262-277
+        lv[0][sl] = a_proc[sl] * lv[0][sl] + (1 - a_proc[sl]) * Er[sl];
+        lv[1][sl] = a_proc[sl] * lv[1][sl] + (1 - a_proc[sl]) * Et[sl];
+        if (ok) {
+          p_num += sqrt(lv[0][sl] * lv[1][sl]);
+          p_den += lv[1][sl];
+          if (loud_frame == UINT_MAX) {   // earmodel.c:890-907
+            const double a = loudfac[sl] * (pow(1. - thres[sl] + thres[sl] * Er[sl] / ethres[sl], 0.23) - 1.);
+            const double c2 = loudfac[sl] * (pow(1. - thres[sl] + thres[sl] * Et[sl] / ethres[sl], 0.23) - 1.);
+            l_r += a > 0. ? a : 0.;
+            l_t += c2 > 0. ? c2 : 0.;
+          }
+        }
+      }
+      p_num = warp_sum(p_num);
+      p_den = warp_sum(p_den);
+      if (loud_frame == UINT_MAX) {
+        l_r = warp_sum(l_r) * (24. / kFbBands);
+        l_t = warp_sum(l_t) * (24. / kFbBands);
+        if (lane == 0 && l_r > 0.1 && l_t > 0.1) sm.latch = 1;   // gstpeaq.c:841-845
+      }
+      const double lev_corr = p_num * p_num / (p_den * p_den);
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        if (lev_corr > 1) {
+          lct[sl] = Et[sl];
+          lcr[sl] = Er[sl] / lev_corr;
+        } else {
+          lcr[sl] = Er[sl];
+          lct[sl] = Et[sl] * lev_corr;
+        }
+        lv[2][sl] = a_proc[sl] * lv[2][sl] + lct[sl] * lcr[sl];
+        lv[3][sl] = a_proc[sl] * lv[3][sl] + lcr[sl] * lcr[sl];
+        double pa_r, pa_t;
+        if (lv[2][sl] >= lv[3][sl]) {
+          pa_r = 1.;
+          pa_t = lv[3][sl] / lv[2][sl];
+        } else {
+          pa_r = lv[2][sl] / lv[3][sl];
+          pa_t = 1.;
+        }
+        if (b < kFbBands) {
+          sm.pa[chan][0][b] = pa_r;
+          sm.pa[chan][1][b] = pa_t;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        const int bb = b < kFbBands ? b : 0;
+        // leveladapter.c:315-339 with band_count 40: m1 = min(k,1), m2 = min(40-k-1,1)
+        const int m1 = min(bb, kFbBands / 36), m2 = min(kFbBands - bb - 1, kFbBands / 25);
+        double ra_r = 0., ra_t = 0.;
+        for (int l = bb - m1; l <= bb + m2; l++) {
+          ra_r += sm.pa[chan][0][l];
+          ra_t += sm.pa[chan][1][l];
+        }
+        ra_r /= (m1 + m2 + 1);
+        ra_t /= (m1 + m2 + 1);
+        lv[4][sl] = a_proc[sl] * lv[4][sl] + (1 - a_proc[sl]) * ra_r;
+        lv[5][sl] = a_proc[sl] * lv[5][sl] + (1 - a_proc[sl]) * ra_t;
+        adr[sl] = lcr[sl] * lv[4][sl];
+        adt[sl] = lct[sl] * lv[5][sl];
+        // modulation (modpatt.c:234-250), ref then test
+        {
+          const double loud = pow(Ur[sl], 0.3);
+          md[0][2][sl] = a_proc[sl] * md[0][2][sl] + (1 - a_proc[sl]) * (deriv_factor * fabs(loud - md[0][0][sl]));
+          md[0][1][sl] = a_proc[sl] * md[0][1][sl] + (1. - a_proc[sl]) * loud;
+          mod_r[sl] = md[0][2][sl] / (1. + md[0][1][sl] / 0.3);
+          md[0][0][sl] = loud;
+          avl_r[sl] = md[0][1][sl];
+        }
+        {
+          const double loud = pow(Ut[sl], 0.3);
+          md[1][2][sl] = a_proc[sl] * md[1][2][sl] + (1 - a_proc[sl]) * (deriv_factor * fabs(loud - md[1][0][sl]));
+          md[1][1][sl] = a_proc[sl] * md[1][1][sl] + (1. - a_proc[sl]) * loud;
+          mod_t[sl] = md[1][2][sl] / (1. + md[1][1][sl] / 0.3);
+          md[1][0][sl] = loud;
+        }
+      }
+    }
+    __syncthreads();   // latch visible
+    if (loud_frame == UINT_MAX && sm.latch) loud_frame = frame_counter;
+
+    // ---- MOVs of the filter-bank clock (gstpeaq.c:987-1007) --------------------
+    if (side == 0) {
+      const bool md_gate = frame_counter >= 125;
+      const bool nl_gate = md_gate && frame_counter - 13 >= loud_frame;
+      double s_md = 0., s_wt = 0., s_nl = 0., s_mc = 0., s_ld = 0.;
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int b = lane + 32 * sl;
+        if (b < kFbBands) {
+          if (md_gate) {   // movs.c:226-242 with levWt = 1 (no second accumulator)
+            const double diff = fabs(mod_r[sl] - mod_t[sl]);
+            s_md += diff / (1. + mod_r[sl]);
+            s_wt += avl_r[sl] / (avl_r[sl] + 1. * in03[sl]);
+          }
+          if (nl_gate) {
+            // peaq_mov_noise_loud_asym (movs.c:551-577): the missing-components
+            // term swaps ref/test patterns AND modulation (settings.h:47)
+            s_nl += nl_term(2.5, 0.3, 1., in_noise[sl], mod_r[sl], mod_t[sl], adr[sl], adt[sl]);
+            s_mc += nl_term(1.5, 0.15, 1., in_noise[sl], mod_t[sl], mod_r[sl], adt[sl], adr[sl]);
+            // peaq_mov_lin_dist (movs.c:679-706): ref modulation on both sides,
+            // adapted ref pattern vs ref excitation
+            s_ld += nl_term(1.5, 0.15, 1., in_noise[sl], mod_r[sl], mod_r[sl], adr[sl], Er[sl]);
+          }
+        }
+      }
+      s_md = warp_sum(s_md);
+      s_wt = warp_sum(s_wt);
+      s_nl = warp_sum(s_nl);
+      s_mc = warp_sum(s_mc);
+      s_ld = warp_sum(s_ld);
+      if (lane == 0) {
+        double (*a)[kAccFields] = sm.acc[chan];
+        // peaq_movaccum_set_tentative on the three fb-clock accumulators (gstpeaq.c:974-979)
+        int st_new = status;
+        if (!above) {
+          if (status == kStNormal) {
+            for (int k = 0; k < 3; k++) {
+              a[k][5] = a[k][0];
+              a[k][6] = a[k][1];
+              a[k][7] = a[k][2];
+            }
+            st_new = kStTentative;
+          }
+        } else {
+          st_new = kStNormal;
+        }
+        if (st_new != kStInit) {
+          if (md_gate) {
+            // MODE_RMS: weight squared (movaccum.c:375-379); value scaled by 100/sqrt(B) (movs.c:243-244)
+            const double val = s_md * (100. / sqrt((double)kFbBands));
+            double w = s_wt;
+            w *= w;
+            a[0][0] += w * val * val;
+            a[0][1] += w;
+          }
+          if (nl_gate) {
+            double nl = s_nl * (24. / kFbBands);
+            if (nl < 0.1) nl = 0.;                       // NLmin (movs.c:740-741)
+            double mc = s_mc * (24. / kFbBands);
+            if (mc < 0.) mc = 0.;
+            double ld = s_ld * (24. / kFbBands);
+            if (ld < 0.) ld = 0.;
+            // MODE_RMS_ASYM (movaccum.c:380-385): field 2 holds the second numerator
+            a[1][0] += nl * nl;
+            a[1][2] += mc * mc;
+            a[1][1] += 1.;
+            a[2][0] += 1. * ld;                          // MODE_AVG, weight 1
+            a[2][1] += 1.;
+          }
+        }
+        if (dbg) {
+          double* d = dbg + (size_t)gridDim.x * n_chunk_frames * 2 * C * 2 * kFbBands +
+                      (((size_t)pair * n_chunk_frames + fl) * C + chan) * 8;
+          double nl = s_nl * (24. / kFbBands);
+          if (nl < 0.1) nl = 0.;
+          d[0] = md_gate ? s_md * (100. / sqrt((double)kFbBands)) : 0.;
+          d[1] = md_gate ? s_wt : 0.;
+          d[2] = nl_gate ? nl : 0.;
+          d[3] = nl_gate ? s_mc * (24. / kFbBands) : 0.;
+          d[4] = nl_gate ? s_ld * (24. / kFbBands) : 0.;
+          d[5] = above;
+        }
+      }
+    }
+    if (!above) {
+      if (status == kStNormal) status = kStTentative;
+    } else {
+      status = kStNormal;
+    }
+    frame_counter++;
+    __syncthreads();
+  }
+
+  // ---- store state, publish the channel-averaged MOVs ----------------------------
+#pragma unroll
+  for (int sl = 0; sl < 2; sl++) {
+    const int b = lane + 32 * sl;
+    if (b < kFbBands) {
+      st_stream[b] = cu[sl];
+      st_stream[kFbBands + b] = exc[sl];
+      for (int i = 0; i < 11; i++) st_stream[(2 + i) * kFbBands + b] = sm.hist[warp][i][b];
+      if (side == 0) {
+        for (int f = 0; f < 6; f++) st[S.off_fb_level + (chan * 6 + f) * kFbBands + b] = lv[f][sl];
+        for (int sd = 0; sd < 2; sd++)
+          for (int f = 0; f < 3; f++)
+            st[S.off_fb_mod + ((chan * 2 + sd) * 3 + f) * kFbBands + b] = md[sd][f][sl];
+      }
+    }
+  }
+  __syncthreads();
+  if (side == 0 && lane < 3 * kAccFields)
+    st[S.off_fb_acc + chan * 3 * kAccFields + lane] = sm.acc[chan][lane / kAccFields][lane % kAccFields];
+  if (threadIdx.x == 0) {
+    st_ints[2] = status;
+    st_ints[3] = (int)frame_counter;
+    st_ints[4] = (int)loud_frame;
+    st_ints[5] = pos;
+    // peaq_movaccum_get_value (movaccum.c:438-481), averaged over channels
+    const bool tent = status == kStTentative;
+    double v0 = 0., v1 = 0., v2 = 0.;
+    for (int c = 0; c < C; c++) {
+      const double (*a)[kAccFields] = sm.acc[c];
+      v0 += sqrt((tent ? a[0][5] : a[0][0]) / (tent ? a[0][6] : a[0][1]));
+      const double den1 = tent ? a[1][6] : a[1][1];
+      v1 += sqrt((tent ? a[1][5] : a[1][0]) / den1);
+      v1 += 0.5 * sqrt((tent ? a[1][7] : a[1][2]) / den1);
+      v2 += (tent ? a[2][5] : a[2][0]) / (tent ? a[2][6] : a[2][1]);
+    }
+    st[S.off_fb_movs] = v0 / C;
+    st[S.off_fb_movs + 1] = v1 / C;
+    st[S.off_fb_movs + 2] = v2 / C;
+  }
+}
+
+// ---------------------------------------------------------------------------
+
+constexpr int kAdvGroup = 64;   // threads per channel (55 bands)
+
+__global__ void __launch_bounds__(kAdvGroup * kMaxChannels)
+adv_fft_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ records,
+                    RecordLayout L, const unsigned* __restrict__ n_frames, unsigned first_frame,
+                    unsigned n_chunk_frames, double* __restrict__ state, AdvStateLayout S,
+                    PairResult* __restrict__ results) {
+  const int C = L.C, B = L.B;
+  const int pair = blockIdx.x;
+  const int c = threadIdx.x / kAdvGroup;
+  const int b = threadIdx.x % kAdvGroup;
+  const int lane = threadIdx.x & 31;
+  const int wig = (threadIdx.x >> 5) & 1;
+  const bool active = b < B;
+  const int bb = active ? b : 0;
+  __shared__ double red[2][kMaxChannels][2];
+  __shared__ double val_sh[kMaxChannels][2];
+
+  double* st = state + (size_t)pair * S.stride;
+  int* st_ints = reinterpret_cast<int*>(st + S.off_ints);
+  double Efr = active ? st[S.off_fft_filtered + c * B + b] : 0.;
+  // accumulator slot owned by thread (c, k): k = 0 SegmentalNMR, 1 EHS; both MODE_AVG
+  double num = 0., den = 0., snum = 0., sden = 0.;
+  const bool acc_thread = b < 2;
+  if (acc_thread) {
+    const double* a = st + S.off_fft_acc + (c * 2 + b) * kAccFields;
+    num = a[0]; den = a[1]; snum = a[5]; sden = a[6];
+  }
+  int status = st_ints[0];
+  unsigned frame_counter = (unsigned)st_ints[1];
+  double sig_energy = st[S.off_fft_scalar], noise_energy = st[S.off_fft_scalar + 1];
+  const double a_ear = T->fft.a_ear[bb], maskdiff = T->maskdiff[bb];
+
+  const unsigned total = n_frames[pair];
+  const unsigned end = min(first_frame + n_chunk_frames, total);
+  for (unsigned f = first_frame; f < end; f++) {
+    const int par = f & 1;
+    const double* rec = records + ((size_t)pair * n_chunk_frames + (f - first_frame)) * L.stride;
+    const int flags = reinterpret_cast<const int*>(rec + L.off_ints)[0];
+    const bool above = flags & kRecFlagAbove;
+    const double E2r = active ? rec[(0 * C + c) * B + b] : 1.;
+    const double nz = active ? rec[L.off_noise + c * B + b] : 0.;
+    Efr = a_ear * Efr + (1. - a_ear) * E2r;                    // fftearmodel.c:496-504
+    const double Er = Efr > E2r ? Efr : E2r;
+    double curr = active ? nz / (Er / maskdiff) : 0.;          // movs.c:1002-1011
+    curr = warp_sum(curr);
+    if (lane == 0) red[par][c][wig] = curr;
+    __syncthreads();
+    if (acc_thread) {
+      if (!above) {
+        if (status == kStNormal) {
+          snum = num;
+          sden = den;
+        }
+      }
+      const int st_new = above ? kStNormal : (status == kStNormal ? kStTentative : status);
+      if (st_new != kStInit) {
+        if (b == 0) {
+          const double nmr = (red[par][c][0] + red[par][c][1]) / B;
+          num += 1. * (10. * log10(nmr));                      // segmental: dB per frame (movs.c:1017-1018)
+          den += 1.;
+        } else if (flags & kRecFlagEhsValid) {
+          num += 1. * (1000. * rec[L.off_ehs + c]);            // movs.c:1441
+          den += 1.;
+        }
+      }
+    }
+    if (!above) {
+      if (status == kStNormal) status = kStTentative;
+    } else {
+      status = kStNormal;
+    }
+    sig_energy += rec[L.off_snr];
+    noise_energy += rec[L.off_snr + 1];
+    frame_counter++;
+  }
+
+  if (active) st[S.off_fft_filtered + c * B + b] = Efr;
+  if (acc_thread) {
+    double* a = st + S.off_fft_acc + (c * 2 + b) * kAccFields;
+    a[0] = num; a[1] = den; a[5] = snum; a[6] = sden;
+    const bool tent = status == kStTentative;
+    val_sh[c][b] = (tent ? snum : num) / (tent ? sden : den);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_ints[0] = status;
+    st_ints[1] = (int)frame_counter;
+    st[S.off_fft_scalar] = sig_energy;
+    st[S.off_fft_scalar + 1] = noise_energy;
+    double movs[5];
+    movs[0] = st[S.off_fb_movs];        // RmsModDiffA
+    movs[1] = st[S.off_fb_movs + 1];    // RmsNoiseLoudAsymA
+    movs[4] = st[S.off_fb_movs + 2];    // AvgLinDistA
+    double v2 = 0., v3 = 0.;
+    for (int cc = 0; cc < C; cc++) {
+      v2 += val_sh[cc][0];
+      v3 += val_sh[cc][1];
+    }
+    movs[2] = v2 / C;                   // SegmentalNMRB
+    movs[3] = v3 / C;                   // EHSB
+    // peaq_calculate_di_advanced (nn.c:304-335)
+    double x[5];
+    for (int j = 0; j < 5; j++) x[j] = T->nn_wxb[j];
+    for (int i = 0; i < 5; i++) {
+      const double m = (movs[i] - T->nn_amin[i]) / (T->nn_amax[i] - T->nn_amin[i]);
+      for (int j = 0; j < 5; j++) x[j] += T->nn_wx[i * 5 + j] * m;
+    }
+    double di = T->nn_wyb;
+    for (int j = 0; j < 5; j++) di += T->nn_wy[j] / (1 + exp(-x[j]));
+    PairResult& r = results[pair];
+    r.di = di;
+    r.odg = -3.98 + (0.22 - -3.98) / (1 + exp(-di));
+    r.totalsnr = 10 * log10(sig_energy / noise_energy);
+    for (int i = 0; i < 11; i++) r.movs[i] = i < 5 ? movs[i] : 0.;
+    r.n_movs = 5;
+    r.frames_fft = frame_counter;
+    r.frames_fb = (unsigned)st_ints[3];
+    r.loudness_reached_frame = (unsigned)st_ints[4];
+  }
+}
+
+// fresh advanced state: zeros, loudness latch unset (gstpeaq.c:359), history slot 10
+__global__ void init_adv_state_kernel(double* state, AdvStateLayout S, int n_pairs) {
+  const size_t total = (size_t)n_pairs * S.stride;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % S.stride);
+    if (o == S.off_ints + 2) {
+      int* ints = reinterpret_cast<int*>(state + i);
+      ints[0] = (int)UINT_MAX;   // slot 4: loudness_reached_frame
+      ints[1] = 10;              // slot 5: newest history entry (next write goes to 0)
+    } else {
+      state[i] = 0.;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_init_adv_state(double* state, AdvStateLayout S, int n_pairs, cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  const size_t total = (size_t)n_pairs * S.stride;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  init_adv_state_kernel<<<blocks, 256, 0, stream>>>(state, S, n_pairs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fb_scan(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
+                           const unsigned char* flags, const unsigned* n_frames, unsigned first_frame,
+                           unsigned n_chunk_frames, double* state, AdvStateLayout S, double* dbg,
+                           int n_pairs, cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  fb_scan_kernel<<<n_pairs, 64 * S.C, 0, stream>>>(d_tables, reinterpret_cast<const double2*>(fbout), n_sub,
+                                                    flags, n_frames, first_frame, n_chunk_frames, state, S,
+                                                    dbg);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adv_fft_scan(const DeviceTables* d_tables, const double* records, RecordLayout L,
+                                const unsigned* n_frames, unsigned first_frame, unsigned n_chunk_frames,
+                                double* state, AdvStateLayout S, PairResult* results, int n_pairs,
+                                cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  adv_fft_scan_kernel<<<n_pairs, kAdvGroup * L.C, 0, stream>>>(d_tables, records, L, n_frames, first_frame,
+                                                               n_chunk_frames, state, S, results);
+  return cudaGetLastError();
+}
+
+}  // namespace peaq

@@ -154,6 +154,49 @@ void fill_fb_model(DeviceTables* t, double playback_level) {
     offset += N / 2 + 1;
   }
   t->fb_tap_offset[kFbBands] = offset;
+  // delay-indexed, full-length, phase-major copy for the polyphase kernel
+  int g = 0;
+  for (int band = 0; band < kFbBands; band++) {
+    const int N = kFbLen[band];
+    const int D = 1 + (kFbLen[0] - N) / 2;          // fbearmodel.c:408
+    const double* hre = t->fb_h_re + t->fb_tap_offset[band];
+    const double* him = t->fb_h_im + t->fb_tap_offset[band];
+    // taps n = 1 .. N-1 (h[0] = h[N] = 0) sit at delays D+1 .. D+N-1.  Band 0
+    // (N = 1456, D = 1): the reference reads delay 1456 from fb_buf[offset+1456],
+    // which aliases the newest sample, i.e. delay 0 (fbearmodel.c:311-313,413).
+    int dlo = D + 1, dhi = D + N - 1;
+    if (dhi >= kFbBuf) {
+      dlo = 0;
+      dhi = kFbBuf - 1;
+    }
+    t->fb_dlo[band] = dlo;
+    t->fb_dhi[band] = dhi;
+    t->fb_g_offset[band] = g;
+    int local = 0;
+    for (int j = 0; j < 32; j++) {
+      t->fb_phase_offset[band * 32 + j] = local;
+      for (int d = j; d <= dhi; d += 32) {
+        if (d < dlo) continue;
+        int dd = d;
+        if (dd == 0 && D + N - 1 >= kFbBuf) dd = kFbBuf;   // the aliased tap
+        const int n = dd - D;
+        double re = 0., im = 0.;
+        if (n >= 1 && n <= N - 1) {
+          if (n <= N / 2) {
+            re = hre[n];
+            im = him[n];
+          } else {
+            re = hre[N - n];     // even symmetry (fbearmodel.c:424)
+            im = -him[N - n];    // odd symmetry (:425)
+          }
+        }
+        t->fb_g[2 * (g + local)] = re;
+        t->fb_g[2 * (g + local) + 1] = im;
+        local++;
+      }
+    }
+    g += local;
+  }
   for (int i = 0; i < 6; i++)
     t->fb_back_mask[i] =
         std::cos(M_PI * (i - 5.) / 12.) * std::cos(M_PI * (i - 5.) / 12.) * 0.9761 / 6.;

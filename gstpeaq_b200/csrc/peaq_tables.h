@@ -18,6 +18,8 @@ constexpr int kFbSub = 32;         // filter bank evaluated every 32 samples (fb
 constexpr int kFbBuf = 1456;       // fbearmodel.c:52
 constexpr int kMaxLag = 256;       // movs.c:42
 constexpr int kFbTapsTotal = 10954; // sum over bands of (N/2+1), N from Table 8 of BS.1387
+constexpr int kFbHist = 1504;      // filtered samples kept in front of a chunk (>= 1456 + 32, multiple of 32)
+constexpr int kFbGTotal = 21868;   // sum over bands of the delay support length (N-1, band 0: N)
 
 struct double2_t { double x, y; };
 
@@ -65,6 +67,15 @@ struct DeviceTables {
   double fb_h_re[kFbTapsTotal];
   double fb_h_im[kFbTapsTotal];
   double fb_back_mask[6];           // fbearmodel.c:179-185
+  // the same filters indexed by total delay d = D + n (D = 1 + (1456-N)/2,
+  // fbearmodel.c:408), full length, phase-major (d = 32 q + j) for the polyphase
+  // kernel: band b covers delays fb_dlo[b]..fb_dhi[b]; its coefficients start at
+  // fb_g_offset[b] (complex entries), phase j at + fb_phase_offset[b*32+j]
+  int fb_dlo[kFbBands];
+  int fb_dhi[kFbBands];
+  int fb_g_offset[kFbBands];
+  int fb_phase_offset[kFbBands * 32];
+  alignas(16) double fb_g[2 * kFbGTotal];
   // neural network (nn.c:40-93)
   double nn_amin[11], nn_amax[11];
   double nn_wx[11 * 5];             // [input][hidden], row stride 5

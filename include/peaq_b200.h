@@ -117,6 +117,12 @@ int peaq_b200_engine_keep_records(peaq_b200_engine *e, int enable);
 int peaq_b200_engine_record_layout(const peaq_b200_engine *e, int32_t *layout9);
 int peaq_b200_engine_copy_records(peaq_b200_engine *e, double *dst, size_t max_doubles,
                                   size_t *n_doubles);
+/* advanced mode, same switch: per 192-sample frame [pair][frame][stream][U|E][40]
+ * (unsmeared / smeared filter-bank excitation; stream = 2*channel + (test?1:0)),
+ * followed by [pair][frame][channel][8] = mod diff, temp weight, noise loudness,
+ * missing components, lin dist, above-threshold flag, 0, 0.  *frames = frames kept. */
+int peaq_b200_engine_copy_fb_debug(peaq_b200_engine *e, double *dst, size_t max_doubles,
+                                   size_t *n_doubles, uint32_t *frames);
 /* constant tables of the engine for a mode / playback level (host code, no
  * GPU needed; same `model`/`which` numbering as the oracle's
  * peaq_oracle_table); returns the count, < 0 on error */

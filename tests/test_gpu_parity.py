@@ -223,3 +223,110 @@ def test_linearity_property_playback_level():
     # thresholds on raw samples (above-threshold, energy flag) are level independent
     # here because the signals are loud; MOVs agree to rounding
     np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------
+# advanced mode (filter-bank ear model + 55-band FFT model, 5 MOVs)
+
+@pytest.fixture(scope="module")
+def engine_adv():
+    e = G.Engine(0, advanced=True)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases().keys()))
+def test_advanced_batch_matches_committed_reference_outputs(engine_adv, golden_ref_outputs, name):
+    ref, test, ch = golden_cases()[name]
+    v = golden_ref_outputs[name + "|advanced"]
+    n = int(v[6])
+    want = {"odg": v[0], "di": v[1], "totalsnr": v[2], "frames_fft": int(v[3]), "frames_fb": int(v[4]),
+            "loudness_reached_frame": int(v[5]), "movs": v[7:7 + n]}
+    out = engine_adv.run_host(ref, test, ch)
+    assert int(out["frames_fb"][0]) == want["frames_fb"]
+    check_result(out[0], want, name)
+
+
+@pytest.mark.parametrize("name", ["synth0_stereo", "noise_silence_stereo", "synth5_mono"])
+def test_advanced_per_frame_filter_bank_matches_oracle(engine_adv, name):
+    ref, test, ch = golden_cases()[name]
+    n = ref.size // ch
+    nfb = (n + 191) // 192
+    o = H.OraclePeaq(True, 92.0, ch, fb_trace=nfb)
+    o.run(ref, test)
+    tr = o.fb_trace
+    engine_adv.keep_records(True)
+    try:
+        engine_adv.run_host(ref, test, ch)
+        exc, movs = engine_adv.fb_debug(1, ch)
+    finally:
+        engine_adv.keep_records(False)
+    np.testing.assert_array_equal(movs[0][:nfb, 0, 5], tr["above_threshold"])     # integer: exact
+    for c in range(ch):
+        for side in range(2):
+            np.testing.assert_allclose(exc[0][:nfb, 2 * c + side, 0], tr["unsmeared"][:, side, c], rtol=1e-9)
+            np.testing.assert_allclose(exc[0][:nfb, 2 * c + side, 1], tr["excitation"][:, side, c], rtol=1e-9)
+    for k, nm in enumerate(["mod_diff", "temp_wt", "noise_loud", "missing_comp", "lin_dist"]):
+        np.testing.assert_allclose(movs[0][:nfb, :, k], tr[nm][:, :ch], rtol=1e-7, atol=1e-9, err_msg=nm)
+
+
+def test_advanced_ragged_batch_and_chunking(engine_adv, monkeypatch):
+    ch = 2
+    lengths = [48000, 30001, 192, 1, 0, 40000, 191, 2048]
+    stride = max(lengths) * ch
+    ref = np.zeros((len(lengths), stride), np.float32)
+    test = np.zeros_like(ref)
+    for p, n in enumerate(lengths):
+        if n:
+            r, t = synth_pair(200 + p, n, ch)
+            ref[p, :n * ch] = r
+            test[p, :n * ch] = t
+    ns = np.array(lengths, np.uint64)
+    out = engine_adv.run_host(ref, test, ch, n_samples=ns)
+    for p, n in enumerate(lengths):
+        want = H.oracle_run_pair(ref[p, :n * ch], test[p, :n * ch], ch, advanced=True)
+        assert int(out["frames_fb"][p]) == want["frames_fb"]
+        check_result(out[p], want, "adv pair %d len %d" % (p, n))
+    monkeypatch.setenv("PEAQ_B200_FB_BUDGET_MB", "1")
+    monkeypatch.setenv("PEAQ_B200_RECORD_BUDGET_MB", "1")
+    e2 = G.Engine(0, advanced=True)
+    try:
+        b = e2.run_host(ref, test, ch, n_samples=ns)
+    finally:
+        e2.close()
+    for k in ("odg", "di", "movs", "frames_fft", "frames_fb", "loudness_reached_frame"):
+        np.testing.assert_array_equal(out[k], b[k])
+
+
+def test_advanced_session_matches_oracle_with_unequal_streams():
+    """element with advanced=TRUE: arbitrary buffers, test stream ends early"""
+    rng = np.random.default_rng(5)
+    ch = 2
+    ref, test = synth_pair(31, 26000, ch)
+    test = test[:ch * 24500]
+    o = H.OraclePeaq(True, 92.0, ch)
+    p = G.Peaq(0, advanced=True, console_output=False)
+    p.set_caps(ch)
+    pr = pt = 0
+    k = 0
+    while pr < ref.size or pt < test.size:
+        a = ch * int(rng.integers(1, 6000))
+        b = ch * int(rng.integers(1, 6000))
+        cr, ct = ref[pr:pr + a], test[pt:pt + b]
+        p.chain_ref(cr)
+        p.chain_test(ct)
+        o.push(cr, ct)
+        pr += a
+        pt += b
+        k += 1
+        if k == 3:      # mid-stream property read
+            mid, want_mid = p.result(), o.result()
+            assert mid["frames_fft"] == want_mid["frames_fft"] and mid["frames_fb"] == want_mid["frames_fb"]
+    res = p.stop()
+    o.finish()
+    want = o.result()
+    assert res["frames_fb"] == want["frames_fb"]
+    got = {"frames_fft": res["frames_fft"], "loudness_reached_frame": res["loudness_reached_frame"],
+           "n_movs": 5, "movs": res["movs"], "di": res["di"], "odg": res["odg"], "totalsnr": res["totalsnr"]}
+    check_result(got, want, "advanced session")
+    p.close()
