@@ -29,6 +29,7 @@ namespace {
 constexpr double kSlopeA = 0.993355506255034;   // fbearmodel.c:49
 constexpr double kDist = 0.921851456499719;     // fbearmodel.c:50
 constexpr double kCl = 0.0802581846102741;      // fbearmodel.c:51
+constexpr double kLnDist = -0.08137117849224008;  // ln(kDist)
 enum { kStInit = 0, kStNormal = 1, kStTentative = 2 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -45,7 +46,8 @@ __device__ __forceinline__ double nl_term(double alpha, double thres_fac, double
   const double stest = thres_fac * test_mod + S0;
   const double beta = exp(-alpha * (ep_test - ep_ref) / ep_ref);
   const double d = stest * ep_test - sref * ep_ref;
-  return pow(ethres / stest, 0.23) * (pow(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta), 0.23) - 1.);
+  return exp(0.23 * log(ethres / stest)) *
+         (exp(0.23 * log(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta))) - 1.);
 }
 
 struct FbSmem {
@@ -135,7 +137,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
           const double L = 10 * log10(o.x * o.x + o.y * o.y);
           const double slope = 24 + 230 / fc[sl] - 0.2 * L;
           const double sl_eff = 4 > slope ? 4 : slope;      // MAX (4, ...), fbearmodel.c:329
-          const double dist_s = pow(kDist, sl_eff);
+          const double dist_s = exp(sl_eff * kLnDist);       // DIST^s
           cu[sl] = cu[sl] + kSlopeA * (dist_s - cu[sl]);
           d1[sl] = o.x;
           d2[sl] = o.y;
@@ -239,8 +241,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
           p_num += sqrt(lv[0][sl] * lv[1][sl]);
           p_den += lv[1][sl];
           if (loud_frame == UINT_MAX) {   // earmodel.c:890-907
-            const double a = loudfac[sl] * (pow(1. - thres[sl] + thres[sl] * Er[sl] / ethres[sl], 0.23) - 1.);
-            const double c2 = loudfac[sl] * (pow(1. - thres[sl] + thres[sl] * Et[sl] / ethres[sl], 0.23) - 1.);
+            const double a = loudfac[sl] * (exp(0.23 * log(1. - thres[sl] + thres[sl] * Er[sl] / ethres[sl])) - 1.);
+            const double c2 = loudfac[sl] * (exp(0.23 * log(1. - thres[sl] + thres[sl] * Et[sl] / ethres[sl])) - 1.);
             l_r += a > 0. ? a : 0.;
             l_t += c2 > 0. ? c2 : 0.;
           }
@@ -299,7 +301,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
         adt[sl] = lct[sl] * lv[5][sl];
         // modulation (modpatt.c:234-250), ref then test
         {
-          const double loud = pow(Ur[sl], 0.3);
+          const double loud = exp(0.3 * log(Ur[sl]));
           md[0][2][sl] = a_proc[sl] * md[0][2][sl] + (1 - a_proc[sl]) * (deriv_factor * fabs(loud - md[0][0][sl]));
           md[0][1][sl] = a_proc[sl] * md[0][1][sl] + (1. - a_proc[sl]) * loud;
           mod_r[sl] = md[0][2][sl] / (1. + md[0][1][sl] / 0.3);
@@ -307,7 +309,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
           avl_r[sl] = md[0][1][sl];
         }
         {
-          const double loud = pow(Ut[sl], 0.3);
+          const double loud = exp(0.3 * log(Ut[sl]));
           md[1][2][sl] = a_proc[sl] * md[1][2][sl] + (1 - a_proc[sl]) * (deriv_factor * fabs(loud - md[1][0][sl]));
           md[1][1][sl] = a_proc[sl] * md[1][1][sl] + (1. - a_proc[sl]) * loud;
           mod_t[sl] = md[1][2][sl] / (1. + md[1][1][sl] / 0.3);

@@ -118,6 +118,7 @@ void fill_fft_model(DeviceTables* t, double playback_level) {
       t->band_wu[band] = u * N / kFs;
     }
     t->aUC[band] = std::pow(10., (-2.4 - 23. / f_c) * t->dz);
+    t->log_aUC[band] = std::log(t->aUC[band]);
     t->gIL[band] = (1. - std::pow(a_low, band + 1)) / (1. - a_low);
     t->spread_norm[band] = 1.;
     t->maskdiff[band] =

@@ -48,18 +48,19 @@ struct DeviceTables {
   double aLe;                       // lower spreading slope ^0.4 (fftearmodel.c:726-728)
   BandTables fft;                   // 109- or 55-band layout
   BandTables fb;                    // 40-band layout
-  double hann[kFftFrame];           // fftearmodel.c:159-173
+  alignas(16) double hann[kFftFrame];  // fftearmodel.c:159-173
   double earw2[kFftBins];           // squared outer/middle ear weight (fftearmodel.c:251-256)
   int band_lo[kMaxBands];           // fftearmodel.c:742-745
   int band_hi[kMaxBands];
   double band_wl[kMaxBands];
   double band_wu[kMaxBands];
   double aUC[kMaxBands];            // fftearmodel.c:765
+  double log_aUC[kMaxBands];        // ln(aUC), for the exp/log form of the spreading slopes
   double gIL[kMaxBands];            // fftearmodel.c:766
   double spread_norm[kMaxBands];    // fftearmodel.c:778-781
   double maskdiff[kMaxBands];       // fftearmodel.c:770-772
   double ehs_window[kMaxLag];       // movs.c:1366-1367
-  double2_t tw1024[768];            // exp(-2 pi i k / 1024), k < 768
+  alignas(16) double2_t tw1024[768];   // exp(-2 pi i k / 1024), k < 768
   double2_t tw2048[kFftBins];       // exp(-2 pi i k / 2048), k <= 1024
   // filter bank (fbearmodel.c:188-225); taps of band b start at fb_tap_offset[b]
   int fb_len[kFbBands];
