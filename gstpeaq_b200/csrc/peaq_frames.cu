@@ -26,6 +26,9 @@
 #include "peaq_engine.h"
 #include "peaq_fft.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 namespace peaq {
 namespace {
 
@@ -63,6 +66,14 @@ __device__ __forceinline__ int warp_max_int(int v) {
 // barrier of the two warps (ref, test) of one channel
 __device__ __forceinline__ void channel_barrier(int chan) {
   asm volatile("bar.sync %0, 64;" ::"r"(chan + 1) : "memory");
+}
+
+// producer / consumer halves of the same barrier (one warp arrives, the other waits)
+__device__ __forceinline__ void channel_arrive(int chan) {
+  asm volatile("bar.arrive %0, 64;" ::"r"(chan + 1 + kMaxChannels) : "memory");
+}
+__device__ __forceinline__ void channel_wait(int chan) {
+  asm volatile("bar.sync %0, 64;" ::"r"(chan + 1 + kMaxChannels) : "memory");
 }
 
 // sample `i` of channel `c` of an interleaved signal, zero past the end
@@ -146,28 +157,55 @@ __device__ __forceinline__ double group_band_noise(const DeviceTables* __restric
 __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* sa, double* se,
                              double* se2, double* __restrict__ out, int lane) {
   const double dz02 = 0.2 * T->dz;
-  for (int i = lane; i < B; i += 32) {
+  // four bands per lane, interleaved for instruction-level parallelism
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const int i = lane + 32 * m;
+    const int ii = i < B ? i : B - 1;
     // aUCE = aUC * Pp^(0.2 dz); gIU = (1 - aUCE^(B-i)) / (1 - aUCE);
     // En = Pp / (gIL + gIU - 1); store aUCE^0.4 and En^0.4   (:647-656)
-    const double pp = se[i];
+    const double pp = i < B ? se[i] : 1.;
     const double lp = log(pp);
-    const double la = T->log_aUC[i] + dz02 * lp;     // ln aUCE
+    const double la = T->log_aUC[ii] + dz02 * lp;     // ln aUCE
     const double a_uce = exp(la);
-    const double g_iu = (1. - exp((double)(B - i) * la)) / (1. - a_uce);
-    const double den = T->gIL[i] + g_iu - 1.;
-    sa[i] = exp(0.4 * la);
-    se[i] = exp(0.4 * (lp - log(den)));
+    const double g_iu = (1. - exp((double)(B - ii) * la)) / (1. - a_uce);
+    const double den = T->gIL[ii] + g_iu - 1.;
+    const double va = exp(0.4 * la);
+    const double ve = exp(0.4 * (lp - log(den)));
+    if (i < B) {   // each lane rewrites only the entry it read
+      sa[i] = va;
+      se[i] = ve;
+    }
   }
   __syncwarp();
   // downward spreading, constant slope: E2[i-1] = aLe * E2[i] + Ene[i-1]   (:658-661)
-  if (lane == 0) {
+  // = sum_{j >= i} aLe^(j-i) Ene[j]: lane l scans bands 4l..4l+3 locally, the lane
+  // carries are combined by a 5-step shuffle scan with the slope raised to 4 * 2^s
+  {
     const double a_le = T->aLe;
-    double acc = se[B - 1];
-    se2[B - 1] = acc;
-    for (int i = B - 1; i > 0; i--) {
-      acc = a_le * acc + se[i - 1];
-      se2[i - 1] = acc;
+    double v[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) v[m] = 4 * lane + m < B ? se[4 * lane + m] : 0.;
+    v[2] = v[2] + a_le * v[3];
+    v[1] = v[1] + a_le * v[2];
+    v[0] = v[0] + a_le * v[1];
+    const double a2 = a_le * a_le, a4 = a2 * a2;
+    double carry = v[0];      // sum over this lane's bands, referred to band 4l
+    double q = a4;            // slope over one lane (4 bands), squared every step
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_down_sync(0xffffffffu, carry, o);
+      if (lane + o < 32) carry = carry + q * up;
+      q = q * q;
     }
+    // contribution of all higher lanes, referred to band 4(l+1)
+    double hi = __shfl_down_sync(0xffffffffu, carry, 1);
+    if (lane == 31) hi = 0.;
+    const double a3 = a2 * a_le;
+    if (4 * lane + 3 < B) se2[4 * lane + 3] = v[3] + a_le * hi;
+    if (4 * lane + 2 < B) se2[4 * lane + 2] = v[2] + a2 * hi;
+    if (4 * lane + 1 < B) se2[4 * lane + 1] = v[1] + a3 * hi;
+    if (4 * lane + 0 < B) se2[4 * lane + 0] = v[0] + a4 * hi;
   }
   __syncwarp();
   // upward spreading (:664-671): source band i adds Ene[i] * aUCEe[i]^(j-i) to every
@@ -180,17 +218,27 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
     r[m] = i < B ? se[i] : 0.;
     a[m] = i < B ? sa[i] : 0.;
   }
-  for (int t = 1; t < B; t++) {
+  // slot m (sources lane + 32 m) only reaches targets below B for t < B - 32 m:
+  // run the step loop in four ranges with 4, 3, 2, 1 live slots
+  auto ladder = [&](int t_begin, int t_end, auto slots) {
+    constexpr int kSlots = decltype(slots)::value;
+    for (int t = t_begin; t < t_end; t++) {
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-      const int j = lane + 32 * m + t;
-      if (j < B) {
-        r[m] *= a[m];
-        se2[j] += r[m];
+      for (int m = 0; m < kSlots; m++) {
+        const int j = lane + 32 * m + t;
+        if (j < B) {
+          r[m] *= a[m];
+          se2[j] += r[m];
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
-  }
+  };
+  const int e3 = B - 96 > 1 ? B - 96 : 1, e2 = B - 64 > 1 ? B - 64 : 1, e1 = B - 32 > 1 ? B - 32 : 1;
+  ladder(1, e3, std::integral_constant<int, 4>());
+  ladder(e3, e2, std::integral_constant<int, 3>());
+  ladder(e2, e1, std::integral_constant<int, 2>());
+  ladder(e1, B, std::integral_constant<int, 1>());
   // E2 = E2s^(1/0.4) / norm  (:673-675); x^2.5 = x^2 sqrt(x)
   for (int i = lane; i < B; i += 32) {
     const double v = se2[i];
@@ -285,7 +333,7 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
 __global__ void __launch_bounds__(128, 3)
 fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned first_frame,
                   unsigned n_chunk_frames, double* __restrict__ records, RecordLayout L, int B,
-                  int advanced) {
+                  int advanced, int debug_stop) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = pcm.channels;
   const int pair = blockIdx.x / n_chunk_frames;
@@ -383,9 +431,11 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     }
   }
   __syncthreads();   // twiddles loaded, flags published (and this warp's scatter complete)
+  if (debug_stop == 1) return;   // development aid: phase timing (PEAQ_B200_K1_STOP)
 
   // ---- 2048-point real FFT, power spectrum into registers --------------------------
   warp_fft<10>(z, tw, lane);
+  if (debug_stop == 2) return;
   double pv[32], p_nyq;
   {
     const double lf = T->level_factor_fft;
@@ -463,10 +513,31 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   }
   if (lane == 0) spec[1024] = p_nyq * T->earw2[1024];
   channel_barrier(chan);   // both spectra of the channel visible
+  if (debug_stop == 3) return;
 
   const double* spec_ref = smem + kTwDoubles + (2 * chan) * kWorkDoubles;
   const double* spec_test = smem + kTwDoubles + (2 * chan + 1) * kWorkDoubles;
   double* dlog = smem + kTwDoubles + (2 * chan + 1) * kWorkDoubles + kScratchDlog;
+
+  // The test warp first does everything that reads BOTH spectra of the channel --
+  // the log spectrum ratio for the EHS (movs.c:1396-1403) and the noise in bands
+  // (movs.c:988-1000) -- and signals it; after that the ref warp may recycle its
+  // buffer for the EHS transforms and never has to wait:
+  //   ref : spreading ......................... -> EHS
+  //   test: ln ratio -> noise in bands -> spreading
+  if (side == 1) {
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+      const int i = lane + 32 * u;
+      const double fref = spec_ref[i], ftest = spec_test[i];
+      dlog[i] = (fref == 0. && ftest == 0.) ? 0. : log(ftest / fref);
+    }
+    for (int i = lane; i < B; i += 32)
+      rec[L.off_noise + chan * B + i] = group_band_noise(T, spec_ref, spec_test, i);
+    __threadfence_block();
+    channel_arrive(chan);
+  }
+  if (debug_stop == 4) return;
 
   // ---- own stream: grouping + internal noise + frequency spreading -----------
   if (!(advanced && side == 1)) {
@@ -475,20 +546,8 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     __syncwarp();
     spread_bands(T, B, work + kScratchA, se, work + kScratchE2, rec + (side * C + chan) * B, lane);
   }
-
-  if (side == 1) {
-    // ---- noise in bands (movs.c:988-1000) ----------------------------------
-    for (int i = lane; i < B; i += 32)
-      rec[L.off_noise + chan * B + i] = group_band_noise(T, spec_ref, spec_test, i);
-    // ---- log spectrum ratio for the EHS (movs.c:1396-1403) -------------------
-#pragma unroll 4
-    for (int u = 0; u < 16; u++) {
-      const int i = lane + 32 * u;
-      const double fref = spec_ref[i], ftest = spec_test[i];
-      dlog[i] = (fref == 0. && ftest == 0.) ? 0. : log(ftest / fref);
-    }
-  }
-  channel_barrier(chan);   // dlog ready; the ref spectrum is no longer needed
+  if (debug_stop == 5) return;
+  if (side == 0) channel_wait(chan);   // ln ratio ready, ref spectrum no longer read by the test warp
 
   bool ehs_valid = false;
   for (int w = 0; w < 2 * C; w++) ehs_valid |= mail_flags[w] != 0;
@@ -528,8 +587,9 @@ cudaError_t launch_fft_frames(const DeviceTables* d_tables, PcmView pcm, int n_p
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)n_chunk_frames * (unsigned)n_pairs);
   dim3 block(64 * pcm.channels);
+  static const int debug_stop = std::getenv("PEAQ_B200_K1_STOP") ? std::atoi(std::getenv("PEAQ_B200_K1_STOP")) : 0;
   fft_frames_kernel<<<grid, block, smem, stream>>>(d_tables, pcm, first_frame, n_chunk_frames, records,
-                                                   L, fft_bands, advanced ? 1 : 0);
+                                                   L, fft_bands, advanced ? 1 : 0, debug_stop);
   return cudaGetLastError();
 }
 
