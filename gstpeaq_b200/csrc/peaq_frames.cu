@@ -76,31 +76,44 @@ __device__ __forceinline__ void channel_wait(int chan) {
   asm volatile("bar.sync %0, 64;" ::"r"(chan + 1 + kMaxChannels) : "memory");
 }
 
+// ---- TMA (cp.async.bulk) staging of one frame of interleaved PCM into shared memory ----
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_global, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_addr(dst_smem)),
+      "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 // sample `i` of channel `c` of an interleaved signal, zero past the end
 __device__ __forceinline__ float pcm_at(const float* __restrict__ sig, unsigned long long s0,
                                         unsigned long long n_samples, int i, int c, int C) {
   const unsigned long long s = s0 + (unsigned long long)i;
   return s < n_samples ? __ldg(sig + s * (unsigned long long)C + c) : 0.0f;
-}
-
-// samples 2n and 2n+1 of channel `chan` (frame-relative)
-__device__ __forceinline__ void load_pair(const float* __restrict__ sig, unsigned long long s0,
-                                          unsigned long long n_samples, int n, int chan, int C,
-                                          bool fast, float* x0, float* x1) {
-  if (fast) {
-    if (C == 2) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(sig + (s0 + 2 * n) * 2));
-      *x0 = chan ? v.y : v.x;
-      *x1 = chan ? v.w : v.z;
-    } else {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(sig + s0 + 2 * n));
-      *x0 = v.x;
-      *x1 = v.y;
-    }
-  } else {
-    *x0 = pcm_at(sig, s0, n_samples, 2 * n, chan, C);
-    *x1 = pcm_at(sig, s0, n_samples, 2 * n + 1, chan, C);
-  }
 }
 
 // literal replay of is_frame_above_threshold for one channel (gstpeaq.c:1088-1096):
@@ -361,23 +374,91 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
   const float* __restrict__ ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
   const float* __restrict__ sig = side ? pcm.test + (size_t)pair * pcm.pair_stride : ref_sig;
-  const bool vec_ok = C <= 2 && (reinterpret_cast<uintptr_t>(sig) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0;
-  const bool fast = vec_ok && s0 + kFftFrame <= n_sig;
-  const bool fast_ref = vec_ok && s0 + kFftFrame <= n_ref;
+  const float* __restrict__ test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  // whole frame inside both signals and 16-byte aligned: stage it with two TMA bulk
+  // copies (ref -> warp 0's buffer, test -> warp 1's buffer, both still unused);
+  // otherwise (last, zero-padded frame; odd strides) fall back to guarded scalar loads
+  const bool tma_ok = C <= 2 && (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(test_sig) & 15) == 0 &&
+                      s0 + kFftFrame <= n_ref && s0 + kFftFrame <= n_test;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(mail + 24);
+  float* raw_ref = reinterpret_cast<float*>(smem + kTwDoubles);
+  float* raw_test = reinterpret_cast<float*>(smem + kTwDoubles + kWorkDoubles);
+  if (tma_ok) {
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned bytes = kFftFrame * C * sizeof(float);
+      mbar_expect_tx(mbar, 2 * bytes);
+      tma_load_1d(raw_ref, ref_sig + s0 * C, bytes, mbar);
+      tma_load_1d(raw_test, test_sig + s0 * C, bytes, mbar);
+    }
+  }
 
-  // ---- load, window, scatter into FFT order; energy; threshold / SNR ------------
+  // ---- phase 1: this stream's 2048 samples into registers; SNR sums ----------------
+  float xs0[32], xs1[32];
+  double energy = 0., es = 0., en = 0.;
+  if (tma_ok) {
+    mbar_wait(mbar, 0);
+    const float* raw = side ? raw_test : raw_ref;
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int n = lane + 32 * u;   // complex index: samples 2n, 2n+1
+      if (C == 2) {
+        const float4 v = *reinterpret_cast<const float4*>(raw + 4 * n);
+        xs0[u] = chan ? v.y : v.x;
+        xs1[u] = chan ? v.w : v.z;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(raw + 2 * n);
+        xs0[u] = v.x;
+        xs1[u] = v.y;
+      }
+      if (side == 1 && u < 16) {
+        // SNR partial sums over the first half of the frame (gstpeaq.c:913-918)
+        float r0, r1;
+        if (C == 2) {
+          const float4 v = *reinterpret_cast<const float4*>(raw_ref + 4 * n);
+          r0 = chan ? v.y : v.x;
+          r1 = chan ? v.w : v.z;
+        } else {
+          const float2 v = *reinterpret_cast<const float2*>(raw_ref + 2 * n);
+          r0 = v.x;
+          r1 = v.y;
+        }
+        es += (double)(r0 * r0);
+        es += (double)(r1 * r1);
+        en += (double)((r0 - xs0[u]) * (r0 - xs0[u]));
+        en += (double)((r1 - xs1[u]) * (r1 - xs1[u]));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int n = lane + 32 * u;
+      xs0[u] = pcm_at(sig, s0, n_sig, 2 * n, chan, C);
+      xs1[u] = pcm_at(sig, s0, n_sig, 2 * n + 1, chan, C);
+      if (side == 1 && u < 16) {
+        const float r0 = pcm_at(ref_sig, s0, n_ref, 2 * n, chan, C);
+        const float r1 = pcm_at(ref_sig, s0, n_ref, 2 * n + 1, chan, C);
+        es += (double)(r0 * r0);
+        es += (double)(r1 * r1);
+        en += (double)((r0 - xs0[u]) * (r0 - xs0[u]));
+        en += (double)((r1 - xs1[u]) * (r1 - xs1[u]));
+      }
+    }
+  }
+  __syncthreads();   // staged PCM consumed: the buffers become FFT work space
+
+  // ---- phase 2: window, scatter into FFT order; energy; threshold --------------------
   double2* z = reinterpret_cast<double2*>(work);
   const int slot_lane = fft_slot_rt<10>(lane);
-  double energy = 0., es = 0., en = 0.;
   bool sure = false, maybe = false;
   float pa0 = 0.f, pa1 = 0.f;   // |x| of the previous iteration (threshold window)
   const float thr_f = 200.f / 32768.f;
 #pragma unroll
   for (int u = 0; u < 32; u++) {
-    const int n = lane + 32 * u;   // complex index: samples 2n, 2n+1
-    float x0, x1;
-    load_pair(sig, s0, n_sig, n, chan, C, fast, &x0, &x1);
+    const int n = lane + 32 * u;
+    const float x0 = xs0[u], x1 = xs1[u];
     const double2 h = *reinterpret_cast<const double2*>(&T->hann[2 * n]);
     z[slot_lane ^ fft_slot<10>(32 * u)] = make_double2(h.x * x0, h.y * x1);
     if (u >= 16) {   // samples 1024..2047: float products, double accumulation (fftearmodel.c:508-511)
@@ -406,14 +487,6 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
       }
       pa0 = a0;
       pa1 = a1;
-    } else if (u < 16) {
-      // SNR partial sums over the first half of the frame (gstpeaq.c:913-918)
-      float r0, r1;
-      load_pair(ref_sig, s0, n_ref, n, chan, C, fast_ref, &r0, &r1);
-      es += (double)(r0 * r0);
-      es += (double)(r1 * r1);
-      en += (double)((r0 - x0) * (r0 - x0));
-      en += (double)((r1 - x1) * (r1 - x1));
     }
   }
   energy = warp_sum(energy);
