@@ -79,37 +79,42 @@ __device__ __forceinline__ double2 fft_tw(const double2* __restrict__ tw, int q)
   return (q & 512) ? make_double2(-w.x, -w.y) : w;
 }
 
-// index contributed by iteration u of a pass (added to the lane part, disjoint bits)
-template <int LQ>
+// Passes are written for NT cooperating threads (32 = one warp, 64 = the two warps
+// of a channel); thread t handles butterflies b = t + NT u.  `Sync` is the barrier
+// of the group (__syncwarp for a warp, a named barrier for two warps).
+struct WarpSync {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+// index contributed by iteration u of a pass (added to the thread part, disjoint bits)
+template <int LQ, int NT>
 __host__ __device__ constexpr int fft_pass_delta(int u) {
-  return LQ <= 32 ? 128 * u : (LQ == 64 ? (32 * (u & 1)) | (256 * (u >> 1)) : 32 * u);
+  return LQ <= NT ? 4 * NT * u : (NT * (u % (LQ / NT))) | (4 * LQ * (u / (LQ / NT)));
 }
 
 // one radix-4 pass; LQ = size of the sub-transforms being combined
-template <int LOG2N, int LQ>
-__device__ __forceinline__ void fft_pass4(double2* z, const double2* __restrict__ tw, int lane) {
+template <int LOG2N, int LQ, int NT, typename Sync>
+__device__ __forceinline__ void fft_pass4(double2* z, const double2* __restrict__ tw, int t, Sync sync) {
   constexpr int N = 1 << LOG2N;
   constexpr int TS = 1024 / (4 * LQ);  // stride into the 1024-point twiddle circle
-  // butterfly b = lane + 32 u combines i0 + {0,1,2,3} LQ with i0 = 4 (b - k) + k, k = b mod LQ
-  const int k_lane = LQ <= 32 ? (lane & (LQ - 1)) : lane;
-  const int base = LQ <= 32 ? ((lane - k_lane) << 2) + k_lane : lane;
+  // butterfly b = t + NT u combines i0 + {0,1,2,3} LQ with i0 = 4 (b - k) + k, k = b mod LQ
+  const int k_t = LQ <= NT ? (t & (LQ - 1)) : t;
+  const int base = LQ <= NT ? ((t - k_t) << 2) + k_t : t;
   const int sb = fft_swz(base);
   double2 w1, w2, w3;
-  if (LQ > 1 && LQ <= 32) {   // twiddles depend on the lane only
-    w1 = tw[k_lane * TS];
-    w2 = tw[2 * k_lane * TS];
-    w3 = fft_tw(tw, 3 * k_lane * TS);
+  if (LQ > 1 && LQ <= NT) {   // twiddles depend on the thread only
+    w1 = tw[k_t * TS];
+    w2 = tw[2 * k_t * TS];
+    w3 = fft_tw(tw, 3 * k_t * TS);
   }
 #pragma unroll
-  for (int u = 0; u < N / 128; u++) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int d = fft_pass_delta<LQ>(u);
+  for (int u = 0; u < N / (4 * NT); u++) {
+    const int d = fft_pass_delta<LQ, NT>(u);
     const int s0 = sb ^ fft_swz(d), s1 = sb ^ fft_swz(d | LQ), s2 = sb ^ fft_swz(d | (2 * LQ)),
               s3 = sb ^ fft_swz(d | (3 * LQ));
     double2 a0 = z[s0], a1 = z[s1], a2 = z[s2], a3 = z[s3];
-    if (LQ > 32) {
-      const int k = LQ == 64 ? (lane | (32 * (u & 1))) : (lane | (32 * u));
+    if (LQ > NT) {
+      const int k = t | (NT * (u % (LQ / NT)));
       w1 = tw[k * TS];
       w2 = tw[2 * k * TS];
       w3 = fft_tw(tw, 3 * k * TS);
@@ -128,41 +133,47 @@ __device__ __forceinline__ void fft_pass4(double2* z, const double2* __restrict_
     z[s2] = make_double2(t0.x - t2.x, t0.y - t2.y);
     z[s3] = make_double2(t1.x - t3.x, t1.y - t3.y);
   }
-  __syncwarp();
+  sync();
 }
 
-template <int LOG2N, int LQ>
+template <int LOG2N, int LQ, int NT, typename Sync>
 struct FftPasses {
-  static __device__ __forceinline__ void run(double2* z, const double2* __restrict__ tw, int lane) {
-    fft_pass4<LOG2N, LQ>(z, tw, lane);
-    FftPasses<LOG2N, LQ * 4>::run(z, tw, lane);
+  static __device__ __forceinline__ void run(double2* z, const double2* __restrict__ tw, int t, Sync sync) {
+    fft_pass4<LOG2N, LQ, NT, Sync>(z, tw, t, sync);
+    FftPasses<LOG2N, LQ * 4, NT, Sync>::run(z, tw, t, sync);
   }
 };
 // recursion ends once LQ reaches 4^(LOG2N/2)
-template <> struct FftPasses<10, 1024> { static __device__ __forceinline__ void run(double2*, const double2*, int) {} };
-template <> struct FftPasses<9, 256> { static __device__ __forceinline__ void run(double2*, const double2*, int) {} };
-template <> struct FftPasses<8, 256> { static __device__ __forceinline__ void run(double2*, const double2*, int) {} };
+template <int NT, typename Sync> struct FftPasses<10, 1024, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
+template <int NT, typename Sync> struct FftPasses<9, 256, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
+template <int NT, typename Sync> struct FftPasses<8, 256, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
 
-// Forward transform (kernel exp(-2 pi i k n / N)).  `tw` = exp(-2 pi i q/1024),
-// q < 512, in shared memory.  Caller must __syncwarp() after filling z.
-template <int LOG2N>
-__device__ __forceinline__ void warp_fft(double2* z, const double2* __restrict__ tw, int lane) {
+// Forward transform (kernel exp(-2 pi i k n / N)) by NT threads.  `tw` =
+// exp(-2 pi i q/1024), q < 512, in shared memory.  The group must be
+// synchronised after filling z; it is synchronised again on return.
+template <int LOG2N, int NT, typename Sync>
+__device__ __forceinline__ void group_fft(double2* z, const double2* __restrict__ tw, int t, Sync sync) {
   constexpr int N = 1 << LOG2N;
-  FftPasses<LOG2N, 1>::run(z, tw, lane);
+  FftPasses<LOG2N, 1, NT, Sync>::run(z, tw, t, sync);
   if (LOG2N % 2 == 1) {
     constexpr int H = N / 2;
     constexpr int TS = 1024 / N;
-    const int sl = fft_swz(lane);
+    const int st = fft_swz(t);
 #pragma unroll
-    for (int u = 0; u < H / 32; u++) {
-      const int se = sl ^ fft_swz(32 * u), so = sl ^ fft_swz(32 * u + H);
+    for (int u = 0; u < H / NT; u++) {
+      const int se = st ^ fft_swz(NT * u), so = st ^ fft_swz(NT * u + H);
       const double2 e = z[se];
-      const double2 o = cmul(z[so], tw[(lane + 32 * u) * TS]);
+      const double2 o = cmul(z[so], tw[(t + NT * u) * TS]);
       z[se] = make_double2(e.x + o.x, e.y + o.y);
       z[so] = make_double2(e.x - o.x, e.y - o.y);
     }
-    __syncwarp();
+    sync();
   }
+}
+
+template <int LOG2N>
+__device__ __forceinline__ void warp_fft(double2* z, const double2* __restrict__ tw, int lane) {
+  group_fft<LOG2N, 32, WarpSync>(z, tw, lane, WarpSync());
 }
 
 }  // namespace peaq
