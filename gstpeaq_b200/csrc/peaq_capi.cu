@@ -153,8 +153,12 @@ struct Engine {
   size_t last_fbdbg_doubles = 0;
   unsigned last_fb_frames = 0;
   size_t fb_budget_bytes = (size_t)24 << 30;
-  float* d_stage[2] = {nullptr, nullptr};
-  size_t stage_cap = 0;     // floats, each
+  float* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [slot][ref|test]
+  size_t stage_cap[2] = {0, 0};   // floats, per buffer of the slot
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_freed[2] = {nullptr, nullptr};
+  std::vector<std::vector<unsigned long long>> plan_hold_ns;   // keep async H2D sources alive
+  std::vector<std::vector<unsigned>> plan_hold_nf;
   std::vector<EventPair> events;
   size_t events_used = 0;
   double ms[5] = {0, 0, 0, 0, 0};
@@ -167,6 +171,11 @@ struct Engine {
   int init() {
     PEAQ_CUDA(cudaSetDevice(device));
     PEAQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    PEAQ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      PEAQ_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+      PEAQ_CUDA(cudaEventCreateWithFlags(&ev_freed[i], cudaEventDisableTiming));
+    }
     h_tables = new (std::nothrow) DeviceTables;
     if (!h_tables) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
     build_tables(h_tables, advanced, level);
@@ -195,8 +204,13 @@ struct Engine {
     cudaFree(d_results);
     cudaFree(d_nsamples);
     cudaFree(d_nframes);
-    cudaFree(d_stage[0]);
-    cudaFree(d_stage[1]);
+    for (int i = 0; i < 2; i++) {
+      cudaFree(d_stage[i][0]);
+      cudaFree(d_stage[i][1]);
+      if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+      if (ev_freed[i]) cudaEventDestroy(ev_freed[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     cudaFree(d_hp);
     cudaFree(d_hp_state);
     cudaFree(d_fbout);
@@ -245,6 +259,16 @@ struct Engine {
     return 0;
   }
 
+  int ensure_stage(int slot, size_t floats) {
+    if (floats <= stage_cap[slot]) return 0;
+    size_t c0 = stage_cap[slot], c1 = stage_cap[slot];
+    int rc;
+    if ((rc = ensure(&d_stage[slot][0], &c0, std::max<size_t>(floats, 4)))) return rc;
+    if ((rc = ensure(&d_stage[slot][1], &c1, std::max<size_t>(floats, 4)))) return rc;
+    stage_cap[slot] = std::min(c0, c1);
+    return 0;
+  }
+
   int ensure_pairs(size_t n_pairs, size_t state_stride, bool preserve_state) {
     if (n_pairs > pairs_cap) {
       if (d_results) PEAQ_CUDA(cudaFree(d_results));
@@ -276,14 +300,19 @@ struct Engine {
   };
 
   int upload_plan(const ClockPlan& plan, int n_pairs, int slot) {
-    std::vector<unsigned long long> a(plan.ns_ref, plan.ns_ref + n_pairs), b(plan.ns_test, plan.ns_test + n_pairs);
-    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot) * pairs_cap, a.data(),
-                              n_pairs * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot + 1) * pairs_cap, b.data(),
-                              n_pairs * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    PEAQ_CUDA(cudaMemcpyAsync(d_nframes + (size_t)slot * pairs_cap, plan.nf, n_pairs * sizeof(unsigned),
+    // the host copies stay alive in plan_hold_* until the batch has been synchronised
+    plan_hold_ns.emplace_back(plan.ns_ref, plan.ns_ref + n_pairs);
+    const unsigned long long* a = plan_hold_ns.back().data();
+    plan_hold_ns.emplace_back(plan.ns_test, plan.ns_test + n_pairs);
+    const unsigned long long* b = plan_hold_ns.back().data();
+    plan_hold_nf.emplace_back(plan.nf, plan.nf + n_pairs);
+    const unsigned* f = plan_hold_nf.back().data();
+    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot) * pairs_cap, a, n_pairs * sizeof(unsigned long long),
                               cudaMemcpyHostToDevice, stream));
-    PEAQ_CUDA(cudaStreamSynchronize(stream));   // the staging vectors die here
+    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot + 1) * pairs_cap, b,
+                              n_pairs * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    PEAQ_CUDA(cudaMemcpyAsync(d_nframes + (size_t)slot * pairs_cap, f, n_pairs * sizeof(unsigned),
+                              cudaMemcpyHostToDevice, stream));
     return 0;
   }
 
@@ -338,7 +367,9 @@ struct Engine {
   // reset_state: start from fresh state (else continue a session).
   int process_resident(const float* d_ref, const float* d_test, size_t pair_stride, int n_pairs,
                        int C, const ClockPlan& fft, const ClockPlan& fb, bool reset_state,
-                       PairResult* h_out) {
+                       PairResult* h_out, PairResult* d_out = nullptr, bool blocking = true) {
+    // d_out: where the kernels write the results (default: the engine's buffer);
+    // blocking = false leaves everything queued on `stream` (finish_batch() later)
     const int B = h_tables->fft_bands;
     const RecordLayout L = make_record_layout(C, B);
     const StateLayout S = make_state_layout(C, B);
@@ -352,6 +383,7 @@ struct Engine {
     }
     if ((rc = upload_plan(fft, n_pairs, 0))) return rc;
     const PcmView pcm = make_view(d_ref, d_test, pair_stride, C, 0);
+    PairResult* d_res = d_out ? d_out : d_results;
 
     if (!advanced) {
       if (reset_state) {
@@ -362,7 +394,7 @@ struct Engine {
         launches++;
       }
       rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first, unsigned n) {
-        return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_results,
+        return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_res,
                                  n_pairs, stream);
       });
       if (rc) return rc;
@@ -417,17 +449,23 @@ struct Engine {
       }
       // ---- FFT clock; its epilogue combines all five MOVs ---------------------------
       rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first_f, unsigned n) {
-        return launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, first_f, n, d_state, A, d_results,
+        return launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, first_f, n, d_state, A, d_res,
                                    n_pairs, stream);
       });
       if (rc) return rc;
     }
 
+    if (!blocking) return 0;
     if (h_out) {
-      PEAQ_CUDA(cudaMemcpyAsync(h_out, d_results, n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost,
-                                stream));
+      PEAQ_CUDA(cudaMemcpyAsync(h_out, d_res, n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost, stream));
     }
+    return finish_batch();
+  }
+
+  int finish_batch() {
     PEAQ_CUDA(cudaStreamSynchronize(stream));
+    plan_hold_ns.clear();
+    plan_hold_nf.clear();
     return timers_collect();
   }
 };
@@ -474,30 +512,47 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     rc = e->process_resident(b->ref, b->test, b->pair_stride, n_pairs, C, fft, fb, true, res);
     if (rc) return rc;
   } else {
-    // host input: stage sub-batches of pairs through device buffers
+    // host input: sub-batches of pairs are staged through two device slots; the
+    // H2D copy of sub-batch i+1 (copy stream) overlaps the kernels of sub-batch i
     const size_t stride = n_pairs > 1 ? b->pair_stride : (size_t)max_n * C;
-    const size_t stage_budget = (size_t)1 << 30;   // floats per staging buffer (4 GiB)
-    int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, stage_budget / std::max<size_t>(stride, 1)));
-    for (int p0 = 0; p0 < n_pairs; p0 += per) {
+    const size_t slot_budget = (size_t)3 << 28;   // floats per staging buffer (3 GiB)
+    int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, slot_budget / std::max<size_t>(stride, 1)));
+    if (per > 592 && n_pairs > 592) per = 592;    // 4 scan CTAs per SM and still several sub-batches
+    PairResult* d_all = nullptr;
+    PEAQ_CUDA(cudaMalloc(&d_all, (size_t)n_pairs * sizeof(PairResult)));
+    int i = 0;
+    for (int p0 = 0; p0 < n_pairs; p0 += per, i++) {
       const int np = std::min(per, n_pairs - p0);
+      const int slot = i & 1;
       const size_t floats = (size_t)(np - 1) * stride + (size_t)max_n * C;
-      size_t cap0 = e->stage_cap, cap1 = e->stage_cap;
-      if ((rc = e->ensure(&e->d_stage[0], &cap0, std::max<size_t>(floats, 4)))) return rc;
-      if ((rc = e->ensure(&e->d_stage[1], &cap1, std::max<size_t>(floats, 4)))) return rc;
-      e->stage_cap = std::min(cap0, cap1);
-      if ((rc = e->timer_begin(3))) return rc;
-      if (floats) {
-        PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[0], b->ref + (size_t)p0 * stride, floats * sizeof(float),
-                                  cudaMemcpyHostToDevice, e->stream));
-        PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[1], b->test + (size_t)p0 * stride, floats * sizeof(float),
-                                  cudaMemcpyHostToDevice, e->stream));
+      if (i >= 2) PEAQ_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_freed[slot], 0));
+      if (floats > e->stage_cap[slot]) {
+        // growing a slot frees memory that queued kernels may still read: drain first
+        PEAQ_CUDA(cudaStreamSynchronize(e->stream));
+        if ((rc = e->ensure_stage(slot, floats))) return rc;
       }
-      if ((rc = e->timer_end())) return rc;
+      if (floats) {
+        PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[slot][0], b->ref + (size_t)p0 * stride, floats * sizeof(float),
+                                  cudaMemcpyHostToDevice, e->copy_stream));
+        PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[slot][1], b->test + (size_t)p0 * stride, floats * sizeof(float),
+                                  cudaMemcpyHostToDevice, e->copy_stream));
+      }
+      PEAQ_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
+      PEAQ_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
       const Engine::ClockPlan fft{ns.data() + p0, ns.data() + p0, nf.data() + p0},
           fb{ns.data() + p0, ns.data() + p0, nfb.data() + p0};
-      rc = e->process_resident(e->d_stage[0], e->d_stage[1], stride, np, C, fft, fb, true, res + p0);
-      if (rc) return rc;
+      rc = e->process_resident(e->d_stage[slot][0], e->d_stage[slot][1], stride, np, C, fft, fb, true, nullptr,
+                               d_all + p0, false);
+      if (rc) {
+        cudaFree(d_all);
+        return rc;
+      }
+      PEAQ_CUDA(cudaEventRecord(e->ev_freed[slot], e->stream));
     }
+    PEAQ_CUDA(cudaMemcpyAsync(res, d_all, (size_t)n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost, e->stream));
+    rc = e->finish_batch();
+    cudaFree(d_all);
+    if (rc) return rc;
   }
   PEAQ_CUDA(cudaEventRecord(t1, e->stream));
   PEAQ_CUDA(cudaEventSynchronize(t1));
@@ -564,16 +619,13 @@ struct Session {
 
   int stage(const float* ref, size_t ref_floats, const float* test, size_t test_floats) {
     const size_t floats = std::max(ref_floats, test_floats);
-    size_t cap0 = engine->stage_cap, cap1 = engine->stage_cap;
     int rc;
-    if ((rc = engine->ensure(&engine->d_stage[0], &cap0, std::max<size_t>(floats, 4)))) return rc;
-    if ((rc = engine->ensure(&engine->d_stage[1], &cap1, std::max<size_t>(floats, 4)))) return rc;
-    engine->stage_cap = std::min(cap0, cap1);
+    if ((rc = engine->ensure_stage(0, floats))) return rc;
     if (ref_floats)
-      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0], ref, ref_floats * sizeof(float), cudaMemcpyHostToDevice,
+      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0][0], ref, ref_floats * sizeof(float), cudaMemcpyHostToDevice,
                                 engine->stream));
     if (test_floats)
-      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[1], test, test_floats * sizeof(float), cudaMemcpyHostToDevice,
+      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0][1], test, test_floats * sizeof(float), cudaMemcpyHostToDevice,
                                 engine->stream));
     return 0;
   }
@@ -587,7 +639,7 @@ struct Session {
     if ((rc = stage(ref, floats, test, floats))) return rc;
     const uint64_t ns = n_samples;
     const Engine::ClockPlan plan{&ns, &ns, &k};
-    rc = engine->process_resident(engine->d_stage[0], engine->d_stage[1], floats, 1, channels, plan, plan,
+    rc = engine->process_resident(engine->d_stage[0][0], engine->d_stage[0][1], floats, 1, channels, plan, plan,
                                   !started, &last);
     if (rc) return rc;
     started = true;
@@ -640,7 +692,7 @@ struct Session {
     clock_plan(nr, nt, kFbFrame, kFbFrame, flushed, &br, &bt, &fbf);
     if ((rc = stage(fifo[0].data(), fifo[0].size(), fifo[1].data(), fifo[1].size()))) return rc;
     const Engine::ClockPlan fft{&fr, &ft, &ff}, fb{&br, &bt, &fbf};
-    rc = engine->process_resident(engine->d_stage[0], engine->d_stage[1],
+    rc = engine->process_resident(engine->d_stage[0][0], engine->d_stage[0][1],
                                   std::max(fifo[0].size(), fifo[1].size()), 1, channels, fft, fb, true, &last);
     if (rc) return rc;
     have_result = true;
