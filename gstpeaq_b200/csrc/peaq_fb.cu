@@ -78,37 +78,10 @@ __global__ void fb_flags_kernel(PcmView pcm, unsigned first_frame, unsigned n_ch
 // ---------------------------------------------------------------------------
 // FB1.  hp buffer per stream: [kFbHist history samples][chunk samples].
 
-__global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams,
-                             unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
-                             double* __restrict__ hp, size_t hp_stride,
-                             double* __restrict__ hp_state /* [stream][6] */, int first_chunk) {
-  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
-  if (stream >= n_streams) return;
-  const int C = pcm.channels;
-  const int pair = stream / (2 * C);
-  const int rem = stream - pair * 2 * C;
-  const int chan = rem >> 1, side = rem & 1;
-  const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
-  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
-  double* __restrict__ out = hp + (size_t)stream * hp_stride;
-  double* st = hp_state + (size_t)stream * 6;
-  // history for the FIR bank: last kFbHist samples of the previous chunk
-  if (first_chunk) {
-    for (int i = 0; i < kFbHist; i++) out[i] = 0.;
-  } else {
-    for (int i = 0; i < kFbHist; i++) out[i] = out[prev_chunk_samples + i];
-  }
-  double x1 = 0, x2 = 0, y1a = 0, y2a = 0, y1b = 0, y2b = 0;
-  if (!first_chunk) {
-    x1 = st[0]; x2 = st[1]; y1a = st[2]; y2a = st[3]; y1b = st[4]; y2b = st[5];
-  }
-  const double lf = T->level_factor_fb;
-  // the item may end inside the chunk: samples past the end are zero (do_flush
-  // pads the last frame, gstpeaq.c:731-736); frames past the padded one are never read
-  for (unsigned i = 0; i < chunk_samples; i++) {
-    const unsigned long long s = t0 + i;
-    const float x = s < n ? __ldg(sig + s * C + chan) : 0.f;
-    const double scaled = x * lf;
+struct Biquads {
+  double x1, x2, y1a, y2a, y1b, y2b;
+  // one sample through the two cascaded DC-reject sections (fbearmodel.c:292-303)
+  __device__ __forceinline__ double step(double scaled) {
     const double h1 = scaled - 2. * x1 + x2 + 1.99517 * y1a - 0.995174 * y2a;
     const double h2 = h1 - 2. * y1a + y2a + 1.99799 * y1b - 0.997998 * y2b;
     x2 = x1;
@@ -117,9 +90,86 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
     y1a = h1;
     y2b = y1b;
     y1b = h2;
-    out[kFbHist + i] = h2;
+    return h2;
   }
-  st[0] = x1; st[1] = x2; st[2] = y1a; st[3] = y2a; st[4] = y1b; st[5] = y2b;
+};
+
+constexpr int kHpBlock = 16;   // samples per register block (input prefetch / 128-byte output rows)
+
+// One thread per (pair, side) runs the C channel filters of that signal in
+// lock step (independent chains => instruction-level parallelism); input is
+// fetched 16 samples ahead with 128-bit loads, output written as full 128-byte
+// rows.  The recurrence itself is inherently sequential in time.
+template <int C>
+__global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_sigs,
+                             unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                             double* __restrict__ hp, size_t hp_stride,
+                             double* __restrict__ hp_state /* [stream][6] */, int first_chunk) {
+  const int sig_idx = blockIdx.x * blockDim.x + threadIdx.x;   // pair * 2 + side
+  if (sig_idx >= n_sigs) return;
+  const int pair = sig_idx >> 1, side = sig_idx & 1;
+  const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
+  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
+  const bool aligned = (reinterpret_cast<uintptr_t>(sig) & 15) == 0;
+  Biquads f[C];
+  double* out[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    const int stream = pair * 2 * C + 2 * c + side;   // stream order of the other kernels
+    out[c] = hp + (size_t)stream * hp_stride;
+    double* st = hp_state + (size_t)stream * 6;
+    if (first_chunk) {
+      f[c] = Biquads{0, 0, 0, 0, 0, 0};
+    } else {
+      f[c] = Biquads{st[0], st[1], st[2], st[3], st[4], st[5]};
+    }
+    // history for the FIR bank: last kFbHist samples of the previous chunk
+    double2* o2 = reinterpret_cast<double2*>(out[c]);
+    if (first_chunk) {
+      for (int i = 0; i < kFbHist / 2; i++) o2[i] = make_double2(0., 0.);
+    } else {
+      const double2* src = reinterpret_cast<const double2*>(out[c] + prev_chunk_samples);
+      for (int i = 0; i < kFbHist / 2; i++) o2[i] = src[i];
+    }
+  }
+  const double lf = T->level_factor_fb;
+  // samples past the end of the item are zero (do_flush pads the last frame,
+  // gstpeaq.c:731-736); frames past the padded one are never read
+  for (unsigned i0 = 0; i0 < chunk_samples; i0 += kHpBlock) {
+    const unsigned long long s = t0 + i0;
+    float x[C][kHpBlock];
+    if (aligned && s + kHpBlock <= n) {
+      const float4* v = reinterpret_cast<const float4*>(sig + s * C);
+#pragma unroll
+      for (int q = 0; q < kHpBlock * C / 4; q++) {
+        const float4 w = __ldg(v + q);
+        const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int r = 0; r < 4; r++) x[(4 * q + r) % C][(4 * q + r) / C] = e[r];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kHpBlock; k++)
+#pragma unroll
+        for (int c = 0; c < C; c++) x[c][k] = s + k < n ? __ldg(sig + (s + k) * C + c) : 0.f;
+    }
+    double y[C][kHpBlock];
+#pragma unroll
+    for (int k = 0; k < kHpBlock; k++)
+#pragma unroll
+      for (int c = 0; c < C; c++) y[c][k] = f[c].step(x[c][k] * lf);   // fbearmodel.c:289
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      double2* o = reinterpret_cast<double2*>(out[c] + kFbHist + i0);
+#pragma unroll
+      for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[c][2 * k], y[c][2 * k + 1]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    double* st = hp_state + (size_t)(pair * 2 * C + 2 * c + side) * 6;
+    st[0] = f[c].x1; st[1] = f[c].x2; st[2] = f[c].y1a; st[3] = f[c].y2a; st[4] = f[c].y1b; st[5] = f[c].y2b;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -223,13 +273,18 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
                          unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
                          double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
                          cudaStream_t stream) {
-  const int n_streams = n_pairs * 2 * pcm.channels;
-  if (n_streams <= 0) return cudaSuccess;
-  // few threads per block so the streams spread over all SMs (latency-bound scan)
+  const int n_sigs = n_pairs * 2;
+  if (n_sigs <= 0) return cudaSuccess;
+  // few threads per block so the signals spread over all SMs (latency-bound scan)
   const int block = 32;
-  fb_hp_kernel<<<(n_streams + block - 1) / block, block, 0, stream>>>(
-      d_tables, pcm, n_streams, t0, chunk_samples, prev_chunk_samples, hp, hp_stride, hp_state,
-      first_chunk ? 1 : 0);
+  const int grid = (n_sigs + block - 1) / block;
+  if (pcm.channels == 2) {
+    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, prev_chunk_samples,
+                                                hp, hp_stride, hp_state, first_chunk ? 1 : 0);
+  } else {
+    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, prev_chunk_samples,
+                                                hp, hp_stride, hp_state, first_chunk ? 1 : 0);
+  }
   return cudaGetLastError();
 }
 

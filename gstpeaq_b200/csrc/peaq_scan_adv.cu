@@ -51,8 +51,6 @@ __device__ __forceinline__ double nl_term(double alpha, double thres_fac, double
 }
 
 struct FbSmem {
-  double a_re[2 * kMaxChannels][kFbBands];
-  double a_im[2 * kMaxChannels][kFbBands];
   double hist[2 * kMaxChannels][11][kFbBands];
   double ex_u[2 * kMaxChannels][kFbBands];
   double ex_e[2 * kMaxChannels][kFbBands];
@@ -117,6 +115,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
     loudfac[sl] = T->fb.loudfac[b];
   }
   const double deriv_factor = (double)48000 / kFbFrame;
+  double cl_to_32 = 1.;   // CL^(32 - lane)
+  for (int i = lane; i < 32; i++) cl_to_32 *= kCl;
   const double2* __restrict__ my_out = fbout + (size_t)stream * kFbBands * n_sub;
 
   const unsigned total = n_frames[pair];
@@ -128,10 +128,12 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
     // ---- six sub-steps of the ear model (fbearmodel.c:314-369) ----------------
     for (int sub = 0; sub < 6; sub++) {
       const unsigned s = fl * 6 + sub;
-      double d1[2], d2[2];
+      // out[band] of this sub-step; lane l holds band l (slot 0) and band 32 + l (slot 1, l < 8)
+      double d1[2], d2[2], are[2], aim[2];
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
+        d1[sl] = d2[sl] = 0.;
         if (b < kFbBands) {
           const double2 o = my_out[(size_t)b * n_sub + s];
           const double L = 10 * log10(o.x * o.x + o.y * o.y);
@@ -141,45 +143,76 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
           cu[sl] = cu[sl] + kSlopeA * (dist_s - cu[sl]);
           d1[sl] = o.x;
           d2[sl] = o.y;
-          sm.a_re[warp][b] = o.x;
-          sm.a_im[warp][b] = o.y;
         }
+        are[sl] = d1[sl];
+        aim[sl] = d2[sl];
       }
-      __syncwarp();
-      // upward spreading: source band b adds out[b] * cu[b]^k to band b + k
+      // upward spreading (fbearmodel.c:339-348): source band b adds out[b] * cu[b]^k to
+      // band b + k.  Each lane advances its own sources (d *= cu); the target lane
+      // fetches step k's contribution from lane - k with a shuffle, wrapping from
+      // slot-0 sources (bands 32+l-k) into the slot-1 targets -- no shared memory,
+      // no barrier, the only serial chain is the multiply.
       for (int k = 1; k < kFbBands; k++) {
-#pragma unroll
-        for (int sl = 0; sl < 2; sl++) {
-          const int b = lane + 32 * sl;
-          if (b + k < kFbBands) {
-            d1[sl] *= cu[sl];
-            d2[sl] *= cu[sl];
-            sm.a_re[warp][b + k] += d1[sl];
-            sm.a_im[warp][b + k] += d2[sl];
+        d1[0] *= cu[0];
+        d2[0] *= cu[0];
+        const int src = (lane - k) & 31;
+        const double v0r = __shfl_sync(0xffffffffu, d1[0], src);
+        const double v0i = __shfl_sync(0xffffffffu, d2[0], src);
+        if (lane >= k) {            // slot-0 target `lane` from slot-0 source lane - k
+          are[0] += v0r;
+          aim[0] += v0i;
+        } else if (lane < 8 && k <= 32 + lane) {   // slot-1 target 32+lane from slot-0 source 32+lane-k
+          are[1] += v0r;
+          aim[1] += v0i;
+        }
+        if (k < 8) {                // slot-1 sources only reach slot-1 targets, k <= 7
+          d1[1] *= cu[1];
+          d2[1] *= cu[1];
+          const double v1r = __shfl_sync(0xffffffffu, d1[1], src);
+          const double v1i = __shfl_sync(0xffffffffu, d2[1], src);
+          if (lane >= k && lane < 8) {
+            are[1] += v1r;
+            aim[1] += v1i;
           }
         }
-        __syncwarp();
       }
-      // downward spreading with the constant slope CL (fbearmodel.c:351-354)
-      if (lane == 0) {
-        double re = sm.a_re[warp][kFbBands - 1], im = sm.a_im[warp][kFbBands - 1];
-        for (int band = kFbBands - 1; band > 0; band--) {
-          re = sm.a_re[warp][band - 1] + kCl * re;
-          im = sm.a_im[warp][band - 1] + kCl * im;
-          sm.a_re[warp][band - 1] = re;
-          sm.a_im[warp][band - 1] = im;
+      // downward spreading with the constant slope CL (fbearmodel.c:351-354):
+      // A[b] = sum_{j >= b} CL^(j-b) A[j], as shuffle scans (slot 1 first, its total
+      // enters slot 0 through band 32)
+      {
+        double q = kCl;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {     // bands 32..39 live in lanes 0..7
+          const double ur = __shfl_down_sync(0xffffffffu, are[1], o);
+          const double ui = __shfl_down_sync(0xffffffffu, aim[1], o);
+          if (lane + o < 8) {
+            are[1] = are[1] + q * ur;
+            aim[1] = aim[1] + q * ui;
+          }
+          q = q * q;
         }
+        const double hr = __shfl_sync(0xffffffffu, are[1], 0);   // A[32] after the scan
+        const double hi = __shfl_sync(0xffffffffu, aim[1], 0);
+        q = kCl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double ur = __shfl_down_sync(0xffffffffu, are[0], o);
+          const double ui = __shfl_down_sync(0xffffffffu, aim[0], o);
+          if (lane + o < 32) {
+            are[0] = are[0] + q * ur;
+            aim[0] = aim[0] + q * ui;
+          }
+          q = q * q;
+        }
+        are[0] = are[0] + cl_to_32 * hr;    // CL^(32 - lane) * A[32]
+        aim[0] = aim[0] + cl_to_32 * hi;
       }
-      __syncwarp();
       // rectification + history (fbearmodel.c:357-368)
       pos = pos == 10 ? 0 : pos + 1;
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
-        if (b < kFbBands) {
-          const double re = sm.a_re[warp][b], im = sm.a_im[warp][b];
-          sm.hist[warp][pos][b] = re * re + im * im;
-        }
+        if (b < kFbBands) sm.hist[warp][pos][b] = are[sl] * are[sl] + aim[sl] * aim[sl];
       }
       __syncwarp();
     }

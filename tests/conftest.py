@@ -15,7 +15,8 @@ def pytest_configure(config):
     # prebuilt files normally travel with the snapshot)
     if not os.path.exists(os.path.join(ROOT, "oracle", "libpeaq_oracle.so")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
-    if not os.path.exists(os.path.join(ROOT, "gstpeaq_b200", "libpeaq_b200.so")):
+    if not (os.path.exists(os.path.join(ROOT, "gstpeaq_b200", "libpeaq_b200.so"))
+            and os.path.exists(os.path.join(ROOT, "gstpeaq_b200", "peaq"))):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "gstpeaq_b200", "csrc")])
     if (not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpeaq_ref.so"))
             and os.path.isdir("/root/reference/src")):

@@ -330,3 +330,56 @@ def test_advanced_session_matches_oracle_with_unequal_streams():
            "n_movs": 5, "movs": res["movs"], "di": res["di"], "odg": res["odg"], "totalsnr": res["totalsnr"]}
     check_result(got, want, "advanced session")
     p.close()
+
+
+# ---------------------------------------------------------------------------
+# long items / batch properties (BASELINE configs[4]: hour-long pairs run as a
+# sequence of chunks with the recurrent state handed over in HBM)
+
+def test_long_item_chunked_matches_oracle(monkeypatch):
+    """2 minutes of audio, records budget of 8 MiB => dozens of K1/K2 chunks"""
+    ch = 2
+    n = 48000 * 120
+    r, t = G.synth_pairs_host(500, 1, n, ch)
+    monkeypatch.setenv("PEAQ_B200_RECORD_BUDGET_MB", "8")
+    e = G.Engine(0, advanced=False)
+    try:
+        out = e.run_host(r, t, ch)
+    finally:
+        e.close()
+    want = H.oracle_run_pair(r[0], t[0], ch)
+    assert int(out["frames_fft"][0]) == G.frames_for_samples(n) == want["frames_fft"]
+    check_result(out[0], want, "2 min item")
+
+
+def test_long_item_advanced_chunked_matches_oracle(monkeypatch):
+    ch = 2
+    n = 48000 * 30
+    r, t = G.synth_pairs_host(501, 1, n, ch)
+    monkeypatch.setenv("PEAQ_B200_FB_BUDGET_MB", "4")
+    monkeypatch.setenv("PEAQ_B200_RECORD_BUDGET_MB", "4")
+    e = G.Engine(0, advanced=True)
+    try:
+        out = e.run_host(r, t, ch)
+    finally:
+        e.close()
+    want = H.oracle_run_pair(r[0], t[0], ch, advanced=True)
+    assert int(out["frames_fb"][0]) == want["frames_fb"] == 7500
+    check_result(out[0], want, "30 s advanced item")
+
+
+def test_batch_properties_order_and_replication(engine):
+    """size-independent properties: results do not depend on the position of a
+    pair in the batch, nor on its neighbours (pairs are closed computations)"""
+    ch = 2
+    r, t = G.synth_pairs_host(600, 7, 30000, ch)
+    a = engine.run_host(r, t, ch)
+    perm = np.array([3, 0, 6, 1, 5, 2, 4])
+    b = engine.run_host(r[perm], t[perm], ch)
+    np.testing.assert_array_equal(a["movs"][perm], b["movs"])
+    np.testing.assert_array_equal(a["odg"][perm], b["odg"])
+    rep = engine.run_host(np.repeat(r[:1], 64, axis=0), np.repeat(t[:1], 64, axis=0), ch)
+    assert np.all(rep["odg"] == a["odg"][0]) and np.all(rep["movs"] == a["movs"][0])
+    # identical signals: noise floor only (NMR at its -118.7 dB class floor, detection probability 0)
+    same = engine.run_host(r[:2], r[:2], ch)
+    assert np.all(same["movs"][:, 9] == 0) and np.all(same["movs"][:, 2] < -100)
