@@ -49,7 +49,9 @@ def frames_per_pair():
 # smoke() that executes anything under oracle/.
 
 def _cpu_worker(args):
-    first, count, kind = args
+    first, count, kind, mode = args
+    global MODE
+    MODE = mode
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import gstpeaq_b200 as G
@@ -60,9 +62,9 @@ def _cpu_worker(args):
     odgs = []
     for p in range(count):
         if kind == "reference":
-            r = H.RefPeaq(False, 92.0, CHANNELS).run(ref[p], test[p])
+            r = H.RefPeaq(MODE == "advanced", 92.0, CHANNELS).run(ref[p], test[p])
         else:
-            r = H.oracle_run_pair(ref[p], test[p], CHANNELS)
+            r = H.oracle_run_pair(ref[p], test[p], CHANNELS, advanced=(MODE == "advanced"))
         frames += r["frames_fft"]
         odgs.append(r["odg"])
     return frames, time.perf_counter() - t0, odgs
@@ -82,7 +84,7 @@ def run_cpu_sample(n_pairs, cores):
     first = 0
     while first < n_pairs:
         c = min(per, n_pairs - first)
-        jobs.append((first, c, kind))
+        jobs.append((first, c, kind, MODE))
         first += c
     ctx = mp.get_context("spawn")
     with ctx.Pool(min(cores, len(jobs))) as pool:
@@ -124,11 +126,14 @@ def reference_arm(args):
     return 0
 
 
+MODE = "basic"
+
+
 def workload_config(n_gpus):
-    return {"workload": "batch=%d synthetic 48 kHz stereo %d s pairs per GPU, basic mode (BASELINE configs[1])"
-                        % (PAIRS_PER_GPU, PAIR_SECONDS),
+    return {"workload": "batch=%d synthetic 48 kHz stereo %d s pairs per GPU, %s mode (BASELINE configs[%d])"
+                        % (PAIRS_PER_GPU, PAIR_SECONDS, MODE, 1 if MODE == "basic" else 2),
             "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus,
-            "frames_per_pair": 468, "channels": CHANNELS, "mode": "basic",
+            "frames_per_pair": 468, "channels": CHANNELS, "mode": MODE,
             "parallelism": "pairs sharded over %d GPU(s), result gather only" % n_gpus,
             "l2": "inputs (31.5 GB per GPU) far exceed the 126 MB L2; no explicit flush"}
 
@@ -229,7 +234,7 @@ def our_arm(args):
     first, count = parallel.shard_range(n_global, rank, world)
     fpp = frames_per_pair()
     L = G.load_library()
-    eng = G.Engine(local_rank, advanced=False)
+    eng = G.Engine(local_rank, advanced=(MODE == "advanced"))
     stride = N_SAMPLES * CHANNELS
     nbytes = count * stride * 4
     dref = G.DeviceBuffer(local_rank, nbytes)
@@ -329,10 +334,10 @@ def our_arm(args):
     # dominant kernel: fft_frames.  algorithmic bytes per launch = 16384 B x frames in the launch;
     # duration = CUDA-event time of the launches (per GPU: frames of one rank)
     frames_rank = count * fpp
-    k1_s = (k1_ms / args.steps) / 1e3
+    k1_s = ((k1_ms if MODE == "basic" else dev_ms) / args.steps) / 1e3
     achieved = frames_rank * BYTES_PER_FRAME / k1_s / 1e9
     traffic = ncu_traffic_per_frame()
-    roofline = {"bound": "hbm", "kernel": "fft_frames_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "fft_frames_kernel" if MODE == "basic" else "fb_bank_kernel + fb_scan_kernel (FP64 bound; HBM figure uses the whole step)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": traffic * frames_rank if traffic else None,
                 "algorithmic_bytes_per_launch_set": frames_rank * BYTES_PER_FRAME,
@@ -372,7 +377,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="basic", choices=["basic", "advanced"],
+                    help="basic = BASELINE configs[1] (default, the headline); advanced = configs[2]")
     args = ap.parse_args()
+    global MODE
+    MODE = args.mode
     if args.impl == "reference":
         return reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -380,7 +389,7 @@ def main():
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--mode", args.mode]
         return subprocess.call(cmd)
     return our_arm(args)
 

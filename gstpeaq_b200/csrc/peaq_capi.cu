@@ -408,7 +408,11 @@ struct Engine {
       const int n_streams = n_pairs * 2 * C;
       const size_t per_frame = (size_t)n_streams * (kFbFrame * sizeof(double) + 6 * kFbBands * 2 * sizeof(double));
       size_t chunk = std::max<unsigned>(max_fb_frames, 1);
-      if (chunk * per_frame > fb_budget_bytes) chunk = std::max<size_t>(fb_budget_bytes / per_frame, 8);
+      if (chunk * per_frame > fb_budget_bytes) {
+        chunk = std::max<size_t>(fb_budget_bytes / per_frame, 8);
+        // 112 frames = 672 sub-steps = 3 FIR tiles of 224: no partially filled tiles
+        if (chunk >= 112) chunk -= chunk % 112;
+      }
       if (keep_records) chunk = std::max<unsigned>(max_fb_frames, 1);
       const size_t hp_stride = kFbHist + chunk * kFbFrame;
       if ((rc = ensure(&d_hp, &hp_cap, (size_t)n_streams * hp_stride))) return rc;

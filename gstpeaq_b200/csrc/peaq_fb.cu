@@ -134,25 +134,40 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   }
   const double lf = T->level_factor_fb;
   // samples past the end of the item are zero (do_flush pads the last frame,
-  // gstpeaq.c:731-736); frames past the padded one are never read
-  for (unsigned i0 = 0; i0 < chunk_samples; i0 += kHpBlock) {
+  // gstpeaq.c:731-736); frames past the padded one are never read.
+  // The raw samples of block i+1 are fetched before block i is filtered, so the
+  // memory latency hides behind the (sequential) recurrence.
+  constexpr int kVec = kHpBlock * C / 4;   // float4 loads per block
+  float4 nxt[kVec];
+  auto fetch = [&](unsigned i0) {
     const unsigned long long s = t0 + i0;
-    float x[C][kHpBlock];
     if (aligned && s + kHpBlock <= n) {
       const float4* v = reinterpret_cast<const float4*>(sig + s * C);
 #pragma unroll
-      for (int q = 0; q < kHpBlock * C / 4; q++) {
-        const float4 w = __ldg(v + q);
-        const float e[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int r = 0; r < 4; r++) x[(4 * q + r) % C][(4 * q + r) / C] = e[r];
-      }
+      for (int q = 0; q < kVec; q++) nxt[q] = __ldg(v + q);
     } else {
 #pragma unroll
-      for (int k = 0; k < kHpBlock; k++)
+      for (int q = 0; q < kVec; q++) {
+        float e[4];
 #pragma unroll
-        for (int c = 0; c < C; c++) x[c][k] = s + k < n ? __ldg(sig + (s + k) * C + c) : 0.f;
+        for (int r = 0; r < 4; r++) {
+          const unsigned long long idx = s * C + 4 * q + r;   // interleaved index
+          e[r] = idx < n * C ? __ldg(sig + idx) : 0.f;
+        }
+        nxt[q] = make_float4(e[0], e[1], e[2], e[3]);
+      }
     }
+  };
+  if (chunk_samples) fetch(0);
+  for (unsigned i0 = 0; i0 < chunk_samples; i0 += kHpBlock) {
+    float x[C][kHpBlock];
+#pragma unroll
+    for (int q = 0; q < kVec; q++) {
+      const float e[4] = {nxt[q].x, nxt[q].y, nxt[q].z, nxt[q].w};
+#pragma unroll
+      for (int r = 0; r < 4; r++) x[(4 * q + r) % C][(4 * q + r) / C] = e[r];
+    }
+    if (i0 + kHpBlock < chunk_samples) fetch(i0 + kHpBlock);
     double y[C][kHpBlock];
 #pragma unroll
     for (int k = 0; k < kHpBlock; k++)
@@ -307,12 +322,9 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
     load[best] += h_tables->fb_len[b] + 64;
   }
   const size_t smem = sizeof(double) * 32 * kRowStride;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fb_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // per device and cheap: set on every launch
+  cudaError_t e = cudaFuncSetAttribute(fb_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   const int n_tiles = (int)((n_sub + kTileOut - 1) / kTileOut);
   fb_bank_kernel<<<(unsigned)n_streams * n_tiles, 32 * kBankWarps, smem, stream>>>(
       d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, bb,

@@ -50,16 +50,22 @@ __device__ __forceinline__ double nl_term(double alpha, double thres_fac, double
          (exp(0.23 * log(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta))) - 1.);
 }
 
+// per-band constants of the filter-bank model, staged in shared memory
+enum { kCFc, kCNoise, kCNoise03, kCAEar, kCAProc, kCEthres, kCThres, kCLoudfac, kCCount };
+
 struct FbSmem {
+  double cst[kCCount][kFbBands];
   double hist[2 * kMaxChannels][11][kFbBands];
   double ex_u[2 * kMaxChannels][kFbBands];
   double ex_e[2 * kMaxChannels][kFbBands];
+  double lv[kMaxChannels][6][kFbBands];       // ref_filt, test_filt, num, den, pc_ref, pc_test
+  double md[kMaxChannels][2][3][kFbBands];    // [ref|test][prev, filt_loud, filt_deriv]
   double pa[kMaxChannels][2][kFbBands];
   double acc[kMaxChannels][3][kAccFields];
   int latch;
 };
 
-__global__ void __launch_bounds__(64 * kMaxChannels)
+__global__ void __launch_bounds__(64 * kMaxChannels, 4)
 fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ fbout,
                unsigned n_sub /* sub-steps per stream in this chunk */,
                const unsigned char* __restrict__ flags, const unsigned* __restrict__ n_frames,
@@ -74,10 +80,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
   double* st = state + (size_t)pair * S.stride;
   int* st_ints = reinterpret_cast<int*>(st + S.off_ints);
 
-  // ---- load state -----------------------------------------------------------
+  // ---- load state and constants -----------------------------------------------
   double cu[2], exc[2];
-  double lv[6][2];       // ref_filt, test_filt, num, den, pc_ref, pc_test (channel warps)
-  double md[2][3][2];    // [ref|test][prev, filt_loud, filt_deriv][slot]      (channel warps)
   double* st_stream = st + S.off_fb_stream + warp * (2 + 11) * kFbBands;
 #pragma unroll
   for (int sl = 0; sl < 2; sl++) {
@@ -85,13 +89,25 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
     const bool ok = b < kFbBands;
     cu[sl] = ok ? st_stream[b] : 0.;
     exc[sl] = ok ? st_stream[kFbBands + b] : 0.;
-    for (int i = 0; i < 11; i++)
-      if (ok) sm.hist[warp][i][b] = st_stream[(2 + i) * kFbBands + b];
-    for (int f = 0; f < 6; f++)
-      lv[f][sl] = (ok && side == 0) ? st[S.off_fb_level + (chan * 6 + f) * kFbBands + b] : 0.;
-    for (int sd = 0; sd < 2; sd++)
-      for (int f = 0; f < 3; f++)
-        md[sd][f][sl] = (ok && side == 0) ? st[S.off_fb_mod + ((chan * 2 + sd) * 3 + f) * kFbBands + b] : 0.;
+    if (ok) {
+      for (int i = 0; i < 11; i++) sm.hist[warp][i][b] = st_stream[(2 + i) * kFbBands + b];
+      if (side == 0) {
+        for (int f = 0; f < 6; f++) sm.lv[chan][f][b] = st[S.off_fb_level + (chan * 6 + f) * kFbBands + b];
+        for (int sd = 0; sd < 2; sd++)
+          for (int f = 0; f < 3; f++)
+            sm.md[chan][sd][f][b] = st[S.off_fb_mod + ((chan * 2 + sd) * 3 + f) * kFbBands + b];
+      }
+      if (warp == 0) {
+        sm.cst[kCFc][b] = T->fb.fc[b];
+        sm.cst[kCNoise][b] = T->fb.internal_noise[b];
+        sm.cst[kCNoise03][b] = T->fb.internal_noise_pow03[b];
+        sm.cst[kCAEar][b] = T->fb.a_ear[b];
+        sm.cst[kCAProc][b] = T->fb.a_proc[b];
+        sm.cst[kCEthres][b] = T->fb.ethres[b];
+        sm.cst[kCThres][b] = T->fb.thres[b];
+        sm.cst[kCLoudfac][b] = T->fb.loudfac[b];
+      }
+    }
   }
   if (side == 0 && lane < 3 * kAccFields)
     sm.acc[chan][lane / kAccFields][lane % kAccFields] = st[S.off_fb_acc + chan * 3 * kAccFields + lane];
@@ -101,19 +117,6 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
   int pos = st_ints[5];          // slot of the newest history entry
   __syncthreads();
 
-  double fc[2], in_noise[2], in03[2], a_ear[2], a_proc[2], ethres[2], thres[2], loudfac[2];
-#pragma unroll
-  for (int sl = 0; sl < 2; sl++) {
-    const int b = min(lane + 32 * sl, kFbBands - 1);
-    fc[sl] = T->fb.fc[b];
-    in_noise[sl] = T->fb.internal_noise[b];
-    in03[sl] = T->fb.internal_noise_pow03[b];
-    a_ear[sl] = T->fb.a_ear[b];
-    a_proc[sl] = T->fb.a_proc[b];
-    ethres[sl] = T->fb.ethres[b];
-    thres[sl] = T->fb.thres[b];
-    loudfac[sl] = T->fb.loudfac[b];
-  }
   const double deriv_factor = (double)48000 / kFbFrame;
   double cl_to_32 = 1.;   // CL^(32 - lane)
   for (int i = lane; i < 32; i++) cl_to_32 *= kCl;
@@ -137,7 +140,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
         if (b < kFbBands) {
           const double2 o = my_out[(size_t)b * n_sub + s];
           const double L = 10 * log10(o.x * o.x + o.y * o.y);
-          const double slope = 24 + 230 / fc[sl] - 0.2 * L;
+          const double slope = 24 + 230 / sm.cst[kCFc][b] - 0.2 * L;
           const double sl_eff = 4 > slope ? 4 : slope;      // MAX (4, ...), fbearmodel.c:329
           const double dist_s = exp(sl_eff * kLnDist);       // DIST^s
           cu[sl] = cu[sl] + kSlopeA * (dist_s - cu[sl]);
@@ -217,11 +220,9 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
       __syncwarp();
     }
     // ---- backward masking, noise, forward masking (fbearmodel.c:371-395) -------
-    double U[2];
 #pragma unroll
     for (int sl = 0; sl < 2; sl++) {
       const int b = lane + 32 * sl;
-      U[sl] = 0.;
       if (b < kFbBands) {
         double e1 = 0.;
         for (int i = 0; i < 5; i++) {
@@ -233,20 +234,15 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
           const int pc_ = pos - 5 < 0 ? pos - 5 + 11 : pos - 5;
           e1 += sm.hist[warp][pc_][b] * T->fb_back_mask[5];
         }
-        U[sl] = e1 + in_noise[sl];
-        exc[sl] = a_ear[sl] * exc[sl] + (1. - a_ear[sl]) * U[sl];
-        sm.ex_u[warp][b] = U[sl];
+        const double U = e1 + sm.cst[kCNoise][b];
+        const double a_ear = sm.cst[kCAEar][b];
+        exc[sl] = a_ear * exc[sl] + (1. - a_ear) * U;
+        sm.ex_u[warp][b] = U;
         sm.ex_e[warp][b] = exc[sl];
-      }
-    }
-    if (dbg) {
-      // [pair][frame][stream][U|E][40]
-      double* d = dbg + (((size_t)pair * n_chunk_frames + fl) * 2 * C + warp) * 2 * kFbBands;
-#pragma unroll
-      for (int sl = 0; sl < 2; sl++) {
-        const int b = lane + 32 * sl;
-        if (b < kFbBands) {
-          d[b] = U[sl];
+        if (dbg) {
+          // [pair][frame][stream][U|E][40]
+          double* d = dbg + (((size_t)pair * n_chunk_frames + fl) * 2 * C + warp) * 2 * kFbBands;
+          d[b] = U;
           d[kFbBands + b] = exc[sl];
         }
       }
@@ -254,28 +250,28 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
     __syncthreads();   // excitations of all streams visible
 
     // ---- channel processing on the ref warp (apply_ear_model_and_preprocess) ----
-    double adr[2], adt[2], mod_r[2], mod_t[2], avl_r[2], Er[2];
+    // per-band values the MOV section needs, kept in registers across the barrier
+    double adr[2], adt[2], mod_r[2], mod_t[2], avl_r[2];
     if (side == 0) {
-      double Et[2], Ur[2], Ut[2], lcr[2], lct[2];
+      double lcr[2], lct[2];
       double p_num = 0., p_den = 0., l_r = 0., l_t = 0.;
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
-        const bool ok = b < kFbBands;
-        const int bb = ok ? b : 0;
-        Er[sl] = sm.ex_e[2 * chan][bb];
-        Et[sl] = sm.ex_e[2 * chan + 1][bb];
-        Ur[sl] = sm.ex_u[2 * chan][bb];
-        Ut[sl] = sm.ex_u[2 * chan + 1][bb];
-        // leveladapter.c:262-277
-        lv[0][sl] = a_proc[sl] * lv[0][sl] + (1 - a_proc[sl]) * Er[sl];
-        lv[1][sl] = a_proc[sl] * lv[1][sl] + (1 - a_proc[sl]) * Et[sl];
-        if (ok) {
-          p_num += sqrt(lv[0][sl] * lv[1][sl]);
-          p_den += lv[1][sl];
+        if (b < kFbBands) {
+          const double a_proc = sm.cst[kCAProc][b];
+          const double Er = sm.ex_e[2 * chan][b], Et = sm.ex_e[2 * chan + 1][b];
+          // leveladapter.c:262-277
+          const double rf = a_proc * sm.lv[chan][0][b] + (1 - a_proc) * Er;
+          const double tf = a_proc * sm.lv[chan][1][b] + (1 - a_proc) * Et;
+          sm.lv[chan][0][b] = rf;
+          sm.lv[chan][1][b] = tf;
+          p_num += sqrt(rf * tf);
+          p_den += tf;
           if (loud_frame == UINT_MAX) {   // earmodel.c:890-907
-            const double a = loudfac[sl] * (exp(0.23 * log(1. - thres[sl] + thres[sl] * Er[sl] / ethres[sl])) - 1.);
-            const double c2 = loudfac[sl] * (exp(0.23 * log(1. - thres[sl] + thres[sl] * Et[sl] / ethres[sl])) - 1.);
+            const double thres = sm.cst[kCThres][b], ethres = sm.cst[kCEthres][b], lfac = sm.cst[kCLoudfac][b];
+            const double a = lfac * (exp(0.23 * log(1. - thres + thres * Er / ethres)) - 1.);
+            const double c2 = lfac * (exp(0.23 * log(1. - thres + thres * Et / ethres)) - 1.);
             l_r += a > 0. ? a : 0.;
             l_t += c2 > 0. ? c2 : 0.;
           }
@@ -292,61 +288,74 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
-        if (lev_corr > 1) {
-          lct[sl] = Et[sl];
-          lcr[sl] = Er[sl] / lev_corr;
-        } else {
-          lcr[sl] = Er[sl];
-          lct[sl] = Et[sl] * lev_corr;
-        }
-        lv[2][sl] = a_proc[sl] * lv[2][sl] + lct[sl] * lcr[sl];
-        lv[3][sl] = a_proc[sl] * lv[3][sl] + lcr[sl] * lcr[sl];
-        double pa_r, pa_t;
-        if (lv[2][sl] >= lv[3][sl]) {
-          pa_r = 1.;
-          pa_t = lv[3][sl] / lv[2][sl];
-        } else {
-          pa_r = lv[2][sl] / lv[3][sl];
-          pa_t = 1.;
-        }
+        lcr[sl] = lct[sl] = 0.;
         if (b < kFbBands) {
-          sm.pa[chan][0][b] = pa_r;
-          sm.pa[chan][1][b] = pa_t;
+          const double a_proc = sm.cst[kCAProc][b];
+          const double Er = sm.ex_e[2 * chan][b], Et = sm.ex_e[2 * chan + 1][b];
+          if (lev_corr > 1) {
+            lct[sl] = Et;
+            lcr[sl] = Er / lev_corr;
+          } else {
+            lcr[sl] = Er;
+            lct[sl] = Et * lev_corr;
+          }
+          const double num = a_proc * sm.lv[chan][2][b] + lct[sl] * lcr[sl];
+          const double den = a_proc * sm.lv[chan][3][b] + lcr[sl] * lcr[sl];
+          sm.lv[chan][2][b] = num;
+          sm.lv[chan][3][b] = den;
+          if (num >= den) {
+            sm.pa[chan][0][b] = 1.;
+            sm.pa[chan][1][b] = den / num;
+          } else {
+            sm.pa[chan][0][b] = num / den;
+            sm.pa[chan][1][b] = 1.;
+          }
         }
       }
       __syncwarp();
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
-        const int bb = b < kFbBands ? b : 0;
-        // leveladapter.c:315-339 with band_count 40: m1 = min(k,1), m2 = min(40-k-1,1)
-        const int m1 = min(bb, kFbBands / 36), m2 = min(kFbBands - bb - 1, kFbBands / 25);
-        double ra_r = 0., ra_t = 0.;
-        for (int l = bb - m1; l <= bb + m2; l++) {
-          ra_r += sm.pa[chan][0][l];
-          ra_t += sm.pa[chan][1][l];
-        }
-        ra_r /= (m1 + m2 + 1);
-        ra_t /= (m1 + m2 + 1);
-        lv[4][sl] = a_proc[sl] * lv[4][sl] + (1 - a_proc[sl]) * ra_r;
-        lv[5][sl] = a_proc[sl] * lv[5][sl] + (1 - a_proc[sl]) * ra_t;
-        adr[sl] = lcr[sl] * lv[4][sl];
-        adt[sl] = lct[sl] * lv[5][sl];
-        // modulation (modpatt.c:234-250), ref then test
-        {
-          const double loud = exp(0.3 * log(Ur[sl]));
-          md[0][2][sl] = a_proc[sl] * md[0][2][sl] + (1 - a_proc[sl]) * (deriv_factor * fabs(loud - md[0][0][sl]));
-          md[0][1][sl] = a_proc[sl] * md[0][1][sl] + (1. - a_proc[sl]) * loud;
-          mod_r[sl] = md[0][2][sl] / (1. + md[0][1][sl] / 0.3);
-          md[0][0][sl] = loud;
-          avl_r[sl] = md[0][1][sl];
-        }
-        {
-          const double loud = exp(0.3 * log(Ut[sl]));
-          md[1][2][sl] = a_proc[sl] * md[1][2][sl] + (1 - a_proc[sl]) * (deriv_factor * fabs(loud - md[1][0][sl]));
-          md[1][1][sl] = a_proc[sl] * md[1][1][sl] + (1. - a_proc[sl]) * loud;
-          mod_t[sl] = md[1][2][sl] / (1. + md[1][1][sl] / 0.3);
-          md[1][0][sl] = loud;
+        adr[sl] = adt[sl] = mod_r[sl] = mod_t[sl] = avl_r[sl] = 0.;
+        if (b < kFbBands) {
+          const double a_proc = sm.cst[kCAProc][b];
+          // leveladapter.c:315-339 with band_count 40: m1 = min(k,1), m2 = min(40-k-1,1)
+          const int m1 = min(b, kFbBands / 36), m2 = min(kFbBands - b - 1, kFbBands / 25);
+          double ra_r = 0., ra_t = 0.;
+          for (int l = b - m1; l <= b + m2; l++) {
+            ra_r += sm.pa[chan][0][l];
+            ra_t += sm.pa[chan][1][l];
+          }
+          ra_r /= (m1 + m2 + 1);
+          ra_t /= (m1 + m2 + 1);
+          const double pcr = a_proc * sm.lv[chan][4][b] + (1 - a_proc) * ra_r;
+          const double pct = a_proc * sm.lv[chan][5][b] + (1 - a_proc) * ra_t;
+          sm.lv[chan][4][b] = pcr;
+          sm.lv[chan][5][b] = pct;
+          adr[sl] = lcr[sl] * pcr;
+          adt[sl] = lct[sl] * pct;
+          // modulation (modpatt.c:234-250), ref then test
+          {
+            const double loud = exp(0.3 * log(sm.ex_u[2 * chan][b]));
+            const double fd = a_proc * sm.md[chan][0][2][b] +
+                              (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][0][0][b]));
+            const double fl_ = a_proc * sm.md[chan][0][1][b] + (1. - a_proc) * loud;
+            sm.md[chan][0][2][b] = fd;
+            sm.md[chan][0][1][b] = fl_;
+            sm.md[chan][0][0][b] = loud;
+            mod_r[sl] = fd / (1. + fl_ / 0.3);
+            avl_r[sl] = fl_;
+          }
+          {
+            const double loud = exp(0.3 * log(sm.ex_u[2 * chan + 1][b]));
+            const double fd = a_proc * sm.md[chan][1][2][b] +
+                              (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][1][0][b]));
+            const double fl_ = a_proc * sm.md[chan][1][1][b] + (1. - a_proc) * loud;
+            sm.md[chan][1][2][b] = fd;
+            sm.md[chan][1][1][b] = fl_;
+            sm.md[chan][1][0][b] = loud;
+            mod_t[sl] = fd / (1. + fl_ / 0.3);
+          }
         }
       }
     }
@@ -362,19 +371,20 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
         if (b < kFbBands) {
+          const double in_noise = sm.cst[kCNoise][b];
           if (md_gate) {   // movs.c:226-242 with levWt = 1 (no second accumulator)
             const double diff = fabs(mod_r[sl] - mod_t[sl]);
             s_md += diff / (1. + mod_r[sl]);
-            s_wt += avl_r[sl] / (avl_r[sl] + 1. * in03[sl]);
+            s_wt += avl_r[sl] / (avl_r[sl] + 1. * sm.cst[kCNoise03][b]);
           }
           if (nl_gate) {
             // peaq_mov_noise_loud_asym (movs.c:551-577): the missing-components
             // term swaps ref/test patterns AND modulation (settings.h:47)
-            s_nl += nl_term(2.5, 0.3, 1., in_noise[sl], mod_r[sl], mod_t[sl], adr[sl], adt[sl]);
-            s_mc += nl_term(1.5, 0.15, 1., in_noise[sl], mod_t[sl], mod_r[sl], adt[sl], adr[sl]);
+            s_nl += nl_term(2.5, 0.3, 1., in_noise, mod_r[sl], mod_t[sl], adr[sl], adt[sl]);
+            s_mc += nl_term(1.5, 0.15, 1., in_noise, mod_t[sl], mod_r[sl], adt[sl], adr[sl]);
             // peaq_mov_lin_dist (movs.c:679-706): ref modulation on both sides,
             // adapted ref pattern vs ref excitation
-            s_ld += nl_term(1.5, 0.15, 1., in_noise[sl], mod_r[sl], mod_r[sl], adr[sl], Er[sl]);
+            s_ld += nl_term(1.5, 0.15, 1., in_noise, mod_r[sl], mod_r[sl], adr[sl], sm.ex_e[2 * chan][b]);
           }
         }
       }
@@ -455,10 +465,10 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
       st_stream[kFbBands + b] = exc[sl];
       for (int i = 0; i < 11; i++) st_stream[(2 + i) * kFbBands + b] = sm.hist[warp][i][b];
       if (side == 0) {
-        for (int f = 0; f < 6; f++) st[S.off_fb_level + (chan * 6 + f) * kFbBands + b] = lv[f][sl];
+        for (int f = 0; f < 6; f++) st[S.off_fb_level + (chan * 6 + f) * kFbBands + b] = sm.lv[chan][f][b];
         for (int sd = 0; sd < 2; sd++)
           for (int f = 0; f < 3; f++)
-            st[S.off_fb_mod + ((chan * 2 + sd) * 3 + f) * kFbBands + b] = md[sd][f][sl];
+            st[S.off_fb_mod + ((chan * 2 + sd) * 3 + f) * kFbBands + b] = sm.md[chan][sd][f][b];
       }
     }
   }
