@@ -367,7 +367,11 @@ struct Engine {
   // reset_state: start from fresh state (else continue a session).
   int process_resident(const float* d_ref, const float* d_test, size_t pair_stride, int n_pairs,
                        int C, const ClockPlan& fft, const ClockPlan& fb, bool reset_state,
-                       PairResult* h_out, PairResult* d_out = nullptr, bool blocking = true) {
+                       PairResult* h_out, PairResult* d_out = nullptr, bool blocking = true,
+                       const float* d_ref_fb = nullptr, const float* d_test_fb = nullptr,
+                       size_t pair_stride_fb = 0) {
+    // d_ref_fb/d_test_fb: separate buffers for the filter-bank clock (streaming sessions
+    // hold different windows of the stream per clock); default: the same buffers
     // d_out: where the kernels write the results (default: the engine's buffer);
     // blocking = false leaves everything queued on `stream` (finish_batch() later)
     const int B = h_tables->fft_bands;
@@ -399,11 +403,13 @@ struct Engine {
       });
       if (rc) return rc;
     } else {
-      if (!reset_state) return fail(PEAQ_B200_ERR_INVALID, "advanced mode runs whole items");
       if ((rc = upload_plan(fb, n_pairs, 1))) return rc;
-      const PcmView pcm_fb = make_view(d_ref, d_test, pair_stride, C, 1);
-      PEAQ_CUDA(launch_init_adv_state(d_state, A, n_pairs, stream));
-      launches++;
+      const PcmView pcm_fb = make_view(d_ref_fb ? d_ref_fb : d_ref, d_test_fb ? d_test_fb : d_test,
+                                       d_ref_fb ? pair_stride_fb : pair_stride, C, 1);
+      if (reset_state) {
+        PEAQ_CUDA(launch_init_adv_state(d_state, A, n_pairs, stream));
+        launches++;
+      }
       // ---- filter-bank clock: chunks of 192-sample frames -----------------------
       const int n_streams = n_pairs * 2 * C;
       const size_t per_frame = (size_t)n_streams * (kFbFrame * sizeof(double) + 6 * kFbBands * 2 * sizeof(double));
@@ -416,7 +422,9 @@ struct Engine {
       if (keep_records) chunk = std::max<unsigned>(max_fb_frames, 1);
       const size_t hp_stride = kFbHist + chunk * kFbFrame;
       if ((rc = ensure(&d_hp, &hp_cap, (size_t)n_streams * hp_stride))) return rc;
-      if ((rc = ensure(&d_hp_state, &hp_state_cap, (size_t)n_streams * 6))) return rc;
+      if ((size_t)n_streams * kHpStateDoubles > hp_state_cap && !reset_state)
+        return fail(PEAQ_B200_ERR_INVALID, "filter state would be lost on growth");
+      if ((rc = ensure(&d_hp_state, &hp_state_cap, (size_t)n_streams * kHpStateDoubles))) return rc;
       if ((rc = ensure(&d_fbout, &fbout_cap, (size_t)n_streams * kFbBands * chunk * 6 * 2))) return rc;
       if ((rc = ensure(&d_fbflags, &fbflags_cap, (size_t)n_pairs * chunk))) return rc;
       double* dbg = nullptr;
@@ -429,23 +437,22 @@ struct Engine {
         last_fbdbg_doubles = need;
         last_fb_frames = (unsigned)chunk;
       }
-      unsigned first = 0, prev_samples = 0;
+      unsigned first = 0;
       while (first < max_fb_frames) {
         const unsigned n = (unsigned)std::min<size_t>(chunk, max_fb_frames - first);
         const unsigned n_sub = n * 6, samples = n * kFbFrame;
         if ((rc = timer_begin(4))) return rc;
         PEAQ_CUDA(launch_fb_flags(pcm_fb, n_pairs, first, n, d_fbflags, stream));
-        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples,
-                               prev_samples, d_hp, hp_stride, d_hp_state, first == 0, stream));
+        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
+                               hp_stride, d_hp_state, first == 0 && reset_state, stream));
         PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, stream));
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbout, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,
                                  dbg, n_pairs, stream));
         launches += 4;
         if ((rc = timer_end())) return rc;
         first += n;
-        prev_samples = samples;
       }
-      if (max_fb_frames == 0) {
+      if (max_fb_frames == 0 && reset_state) {
         // publish the (empty) fb-clock MOVs so the epilogue sees 0/0 like the reference
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbout, 0, d_fbflags, pcm_fb.n_frames, 0, 0, d_state, A, nullptr,
                                  n_pairs, stream));
@@ -577,23 +584,18 @@ struct Session {
   double level = 92.0;
   int channels = 0;
   Engine* engine = nullptr;
-  bool started = false;          // basic mode: state initialised on the device
-  // basic mode: GstAdapter stand-ins (ref_adapter_fft / test_adapter_fft), drained as
-  // frames complete.  advanced mode: the whole item is kept (both clocks re-read it)
-  // and evaluated on demand -- see get_result / finish.
-  std::vector<float> fifo[2];
+  bool started = false;          // recurrent state initialised on the device
+  // GstAdapter stand-ins: [0] FFT clock (ref_adapter_fft / test_adapter_fft), [1] filter-bank
+  // clock (ref_adapter_fb / test_adapter_fb, advanced mode only; gstpeaq.c:116-119, :626-635)
+  std::vector<float> fifo[2][2];   // [clock][ref|test]
   PairResult last = {};
   bool have_result = false;
-  bool dirty = false;            // advanced: samples arrived since `last` was computed
-  bool flushed = false;          // advanced: finish() seen (one padded frame per clock)
 
   void reset_stream() {
     started = false;
     have_result = false;
-    dirty = false;
-    flushed = false;
-    fifo[0].clear();
-    fifo[1].clear();
+    for (auto& c : fifo)
+      for (auto& f : c) f.clear();
   }
 
   void drop_engine() {
@@ -621,87 +623,93 @@ struct Session {
     return rc;
   }
 
-  int stage(const float* ref, size_t ref_floats, const float* test, size_t test_floats) {
-    const size_t floats = std::max(ref_floats, test_floats);
+  int stage(int slot, const float* ref, const float* test, size_t floats) {
     int rc;
-    if ((rc = engine->ensure_stage(0, floats))) return rc;
-    if (ref_floats)
-      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0][0], ref, ref_floats * sizeof(float), cudaMemcpyHostToDevice,
+    if ((rc = engine->ensure_stage(slot, floats))) return rc;
+    if (floats) {
+      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[slot][0], ref, floats * sizeof(float), cudaMemcpyHostToDevice,
                                 engine->stream));
-    if (test_floats)
-      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[0][1], test, test_floats * sizeof(float), cudaMemcpyHostToDevice,
+      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[slot][1], test, floats * sizeof(float), cudaMemcpyHostToDevice,
                                 engine->stream));
+    }
     return 0;
   }
 
-  // basic mode: run `k` frames over the first n_samples samples of both buffers
-  int run_frames(unsigned k, const float* ref, const float* test, size_t n_samples) {
+  // Runs k_fft frames of the FFT clock over the first n_fft samples of (ref_fft, test_fft)
+  // and k_fb frames of the filter-bank clock over the first n_fb samples of (ref_fb, test_fb),
+  // continuing from the state on the device.
+  int run_frames(unsigned k_fft, const float* ref_fft, const float* test_fft, size_t n_fft, unsigned k_fb,
+                 const float* ref_fb, const float* test_fb, size_t n_fb) {
     int rc = ensure_engine();
     if (rc) return rc;
     PEAQ_CUDA(cudaSetDevice(device));
-    const size_t floats = n_samples * channels;
-    if ((rc = stage(ref, floats, test, floats))) return rc;
-    const uint64_t ns = n_samples;
-    const Engine::ClockPlan plan{&ns, &ns, &k};
-    rc = engine->process_resident(engine->d_stage[0][0], engine->d_stage[0][1], floats, 1, channels, plan, plan,
-                                  !started, &last);
+    const size_t fl_fft = n_fft * channels, fl_fb = n_fb * channels;
+    if ((rc = stage(0, ref_fft, test_fft, fl_fft))) return rc;
+    if (advanced && (rc = stage(1, ref_fb, test_fb, fl_fb))) return rc;
+    const uint64_t ns_fft = n_fft, ns_fb = n_fb;
+    const Engine::ClockPlan fft{&ns_fft, &ns_fft, &k_fft}, fb{&ns_fb, &ns_fb, &k_fb};
+    rc = engine->process_resident(engine->d_stage[0][0], engine->d_stage[0][1], std::max<size_t>(fl_fft, 1), 1,
+                                  channels, fft, fb, !started, &last, nullptr, true,
+                                  advanced ? engine->d_stage[1][0] : nullptr,
+                                  advanced ? engine->d_stage[1][1] : nullptr, std::max<size_t>(fl_fb, 1));
     if (rc) return rc;
     started = true;
     have_result = true;
     return 0;
   }
 
-  // do_processing (gstpeaq.c:596-611), basic mode
-  int drain() {
-    const size_t fl = std::min(fifo[0].size(), fifo[1].size());
-    const size_t frame = (size_t)kFftFrame * channels, step = (size_t)kFftStep * channels;
-    if (fl < frame) return 0;
-    const unsigned k = (unsigned)((fl - frame) / step + 1);
-    const size_t n_samples = (size_t)(k - 1) * kFftStep + kFftFrame;
-    int rc = run_frames(k, fifo[0].data(), fifo[1].data(), n_samples);
-    if (rc) return rc;
-    for (int s = 0; s < 2; s++) fifo[s].erase(fifo[s].begin(), fifo[s].begin() + (size_t)k * step);
-    return 0;
-  }
-
-  // What one clock (frame size F, step St) has processed of streams of nr / nt
-  // samples: do_processing runs while BOTH hold a frame; do_flush (if `flush`)
-  // adds one zero-padded frame made of MIN(left, F) samples of each stream.
-  static void clock_plan(uint64_t nr, uint64_t nt, unsigned F, unsigned St, bool flush, uint64_t* er,
-                         uint64_t* et, unsigned* frames) {
-    const uint64_t m = std::min(nr, nt);
-    const uint64_t k = m >= F ? (m - F) / St + 1 : 0;
-    uint64_t lr = nr - k * St, lt = nt - k * St;   // left in the adapters
-    unsigned f = (unsigned)k;
-    uint64_t use_r = k ? (k - 1) * St + F : 0, use_t = use_r;
-    if (flush && (lr || lt)) {
-      use_r = k * St + std::min<uint64_t>(lr, F);
-      use_t = k * St + std::min<uint64_t>(lt, F);
-      f += 1;
+  // whole frames available on one clock (do_processing, gstpeaq.c:596-611)
+  unsigned frames_ready(int clock, unsigned F, unsigned St, size_t* n_samples) const {
+    const size_t fl = std::min(fifo[clock][0].size(), fifo[clock][1].size());
+    const size_t frame = (size_t)F * channels, step = (size_t)St * channels;
+    if (fl < frame) {
+      *n_samples = 0;
+      return 0;
     }
-    *er = std::min(use_r, nr);
-    *et = std::min(use_t, nt);
-    *frames = f;
+    const unsigned k = (unsigned)((fl - frame) / step + 1);
+    *n_samples = (size_t)(k - 1) * St + F;
+    return k;
   }
 
-  // advanced mode: evaluate everything received so far
-  int evaluate_advanced() {
-    int rc = ensure_engine();
+  void consume(int clock, unsigned k, unsigned St) {
+    const size_t n = (size_t)k * St * channels;
+    for (int s = 0; s < 2; s++) fifo[clock][s].erase(fifo[clock][s].begin(), fifo[clock][s].begin() + n);
+  }
+
+  // pad_chain's processing part (gstpeaq.c:637-656): drain both clocks
+  int drain() {
+    size_t n_fft = 0, n_fb = 0;
+    const unsigned k_fft = frames_ready(0, kFftFrame, kFftStep, &n_fft);
+    const unsigned k_fb = advanced ? frames_ready(1, kFbFrame, kFbFrame, &n_fb) : 0;
+    if (k_fft == 0 && k_fb == 0) return 0;
+    int rc = run_frames(k_fft, fifo[0][0].data(), fifo[0][1].data(), n_fft, k_fb, fifo[1][0].data(),
+                        fifo[1][1].data(), n_fb);
     if (rc) return rc;
-    PEAQ_CUDA(cudaSetDevice(device));
-    const uint64_t nr = fifo[0].size() / channels, nt = fifo[1].size() / channels;
-    uint64_t fr, ft, br, bt;
-    unsigned ff, fbf;
-    clock_plan(nr, nt, kFftFrame, kFftStep, flushed, &fr, &ft, &ff);
-    clock_plan(nr, nt, kFbFrame, kFbFrame, flushed, &br, &bt, &fbf);
-    if ((rc = stage(fifo[0].data(), fifo[0].size(), fifo[1].data(), fifo[1].size()))) return rc;
-    const Engine::ClockPlan fft{&fr, &ft, &ff}, fb{&br, &bt, &fbf};
-    rc = engine->process_resident(engine->d_stage[0][0], engine->d_stage[0][1],
-                                  std::max(fifo[0].size(), fifo[1].size()), 1, channels, fft, fb, true, &last);
-    if (rc) return rc;
-    have_result = true;
-    dirty = false;
+    consume(0, k_fft, kFftStep);
+    if (advanced) consume(1, k_fb, kFbFrame);
     return 0;
+  }
+
+  // do_flush (gstpeaq.c:716-745) on both clocks: ONE zero-padded frame per adapter
+  // pair made of MIN(left, frame) samples of each stream
+  int flush() {
+    std::vector<float> pad[2][2];
+    unsigned k[2] = {0, 0};
+    const unsigned F[2] = {kFftFrame, kFbFrame};
+    for (int c = 0; c < (advanced ? 2 : 1); c++) {
+      if (fifo[c][0].empty() && fifo[c][1].empty()) continue;
+      const size_t frame = (size_t)F[c] * channels;
+      for (int s = 0; s < 2; s++) {
+        pad[c][s].assign(frame, 0.f);
+        const size_t n = std::min(fifo[c][s].size(), frame);
+        std::copy(fifo[c][s].begin(), fifo[c][s].begin() + n, pad[c][s].begin());
+        fifo[c][s].erase(fifo[c][s].begin(), fifo[c][s].begin() + n);
+      }
+      k[c] = 1;
+    }
+    if (!k[0] && !k[1]) return 0;
+    return run_frames(k[0], pad[0][0].data(), pad[0][1].data(), k[0] ? kFftFrame : 0, k[1], pad[1][0].data(),
+                      pad[1][1].data(), k[1] ? kFbFrame : 0);
   }
 };
 
@@ -965,11 +973,8 @@ int peaq_b200_session_push(peaq_b200_session* h, int pad, const float* data, siz
   if (pad != PEAQ_B200_PAD_REF && pad != PEAQ_B200_PAD_TEST) return fail(PEAQ_B200_ERR_INVALID, "bad pad");
   Session* s = reinterpret_cast<Session*>(h);
   if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
-  s->fifo[pad].insert(s->fifo[pad].end(), data, data + n * s->channels);
-  if (s->advanced) {
-    s->dirty = true;   // evaluated lazily: both clocks re-read the whole item
-    return 0;
-  }
+  s->fifo[0][pad].insert(s->fifo[0][pad].end(), data, data + n * s->channels);
+  if (s->advanced) s->fifo[1][pad].insert(s->fifo[1][pad].end(), data, data + n * s->channels);
   return s->drain();
 }
 
@@ -977,34 +982,14 @@ int peaq_b200_session_finish(peaq_b200_session* h) {
   if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   Session* s = reinterpret_cast<Session*>(h);
   if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
-  if (s->advanced) {
-    s->flushed = true;
-    return s->evaluate_advanced();
-  }
   int rc = s->drain();
   if (rc) return rc;
-  // do_flush (gstpeaq.c:716-745): one zero-padded frame from whatever is left
-  if (!s->fifo[0].empty() || !s->fifo[1].empty()) {
-    const size_t frame = (size_t)kFftFrame * s->channels;
-    std::vector<float> pr(frame, 0.f), pt(frame, 0.f);
-    const size_t nr = std::min(s->fifo[0].size(), frame), nt = std::min(s->fifo[1].size(), frame);
-    std::copy(s->fifo[0].begin(), s->fifo[0].begin() + nr, pr.begin());
-    std::copy(s->fifo[1].begin(), s->fifo[1].begin() + nt, pt.begin());
-    rc = s->run_frames(1, pr.data(), pt.data(), kFftFrame);
-    if (rc) return rc;
-    s->fifo[0].erase(s->fifo[0].begin(), s->fifo[0].begin() + nr);
-    s->fifo[1].erase(s->fifo[1].begin(), s->fifo[1].begin() + nt);
-  }
-  return 0;
+  return s->flush();
 }
 
 int peaq_b200_session_get_result(peaq_b200_session* h, peaq_b200_result* out) {
   if (!h || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   Session* s = reinterpret_cast<Session*>(h);
-  if (s->advanced && s->dirty && s->channels) {
-    int rc = s->evaluate_advanced();
-    if (rc) return rc;
-  }
   if (!s->have_result) {
     // no frame processed yet: the reference would evaluate empty accumulators
     // (0/0); report that state without touching the GPU

@@ -21,6 +21,7 @@ constexpr int kMaxChannels = 2;
 constexpr int kNumAcc = 11;        // accumulator slots (11 basic MOVs; 5 used in advanced)
 constexpr int kAccFields = 8;      // num, den, x0, x1, x2, saved num, saved den, saved max
 constexpr int kBandStateFields = 14;
+constexpr int kHpStateDoubles = 6 + kFbHist;   // DC-reject filter state + FIR history per stream (even: 16-byte rows)
 
 // Layout of one per-frame record written by K1 and read by K2 (units: doubles).
 struct RecordLayout {
@@ -151,7 +152,7 @@ size_t fft_frames_smem_bytes(int channels);
 cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsigned n_chunk_frames,
                             unsigned char* flags, cudaStream_t stream);
 cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
-                         unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                         unsigned long long t0, unsigned chunk_samples,
                          double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
                          cudaStream_t stream);
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,

@@ -102,9 +102,9 @@ constexpr int kHpBlock = 16;   // samples per register block (input prefetch / 1
 // rows.  The recurrence itself is inherently sequential in time.
 template <int C>
 __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_sigs,
-                             unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                             unsigned long long t0, unsigned chunk_samples,
                              double* __restrict__ hp, size_t hp_stride,
-                             double* __restrict__ hp_state /* [stream][6] */, int first_chunk) {
+                             double* __restrict__ hp_state /* [stream][kHpStateDoubles] */, int first_chunk) {
   const int sig_idx = blockIdx.x * blockDim.x + threadIdx.x;   // pair * 2 + side
   if (sig_idx >= n_sigs) return;
   const int pair = sig_idx >> 1, side = sig_idx & 1;
@@ -117,7 +117,7 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   for (int c = 0; c < C; c++) {
     const int stream = pair * 2 * C + 2 * c + side;   // stream order of the other kernels
     out[c] = hp + (size_t)stream * hp_stride;
-    double* st = hp_state + (size_t)stream * 6;
+    double* st = hp_state + (size_t)stream * kHpStateDoubles;
     if (first_chunk) {
       f[c] = Biquads{0, 0, 0, 0, 0, 0};
     } else {
@@ -128,7 +128,7 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
     if (first_chunk) {
       for (int i = 0; i < kFbHist / 2; i++) o2[i] = make_double2(0., 0.);
     } else {
-      const double2* src = reinterpret_cast<const double2*>(out[c] + prev_chunk_samples);
+      const double2* src = reinterpret_cast<const double2*>(st + 6);   // saved by the previous chunk
       for (int i = 0; i < kFbHist / 2; i++) o2[i] = src[i];
     }
   }
@@ -182,8 +182,13 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   }
 #pragma unroll
   for (int c = 0; c < C; c++) {
-    double* st = hp_state + (size_t)(pair * 2 * C + 2 * c + side) * 6;
+    double* st = hp_state + (size_t)(pair * 2 * C + 2 * c + side) * kHpStateDoubles;
     st[0] = f[c].x1; st[1] = f[c].x2; st[2] = f[c].y1a; st[3] = f[c].y2a; st[4] = f[c].y1b; st[5] = f[c].y2b;
+    // the last kFbHist filtered samples ([history | chunk] is contiguous in `out`) become
+    // the next chunk's history; works for chunks shorter than the history too
+    double2* dst = reinterpret_cast<double2*>(st + 6);
+    const double2* src = reinterpret_cast<const double2*>(out[c] + chunk_samples);
+    for (int i = 0; i < kFbHist / 2; i++) dst[i] = src[i];
   }
 }
 
@@ -285,7 +290,7 @@ cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsi
 }
 
 cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
-                         unsigned long long t0, unsigned chunk_samples, unsigned prev_chunk_samples,
+                         unsigned long long t0, unsigned chunk_samples,
                          double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
                          cudaStream_t stream) {
   const int n_sigs = n_pairs * 2;
@@ -294,11 +299,11 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
   const int block = 32;
   const int grid = (n_sigs + block - 1) / block;
   if (pcm.channels == 2) {
-    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, prev_chunk_samples,
-                                                hp, hp_stride, hp_state, first_chunk ? 1 : 0);
+    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, hp, hp_stride, hp_state,
+                                                first_chunk ? 1 : 0);
   } else {
-    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, prev_chunk_samples,
-                                                hp, hp_stride, hp_state, first_chunk ? 1 : 0);
+    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, hp, hp_stride, hp_state,
+                                                first_chunk ? 1 : 0);
   }
   return cudaGetLastError();
 }

@@ -383,3 +383,37 @@ def test_batch_properties_order_and_replication(engine):
     # identical signals: noise floor only (NMR at its -118.7 dB class floor, detection probability 0)
     same = engine.run_host(r[:2], r[:2], ch)
     assert np.all(same["movs"][:, 9] == 0) and np.all(same["movs"][:, 2] < -100)
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_session_tiny_buffers_and_midstream_reads(advanced):
+    """buffers much smaller than a frame (and than the FIR history of the
+    filter bank); every few pushes the running result must equal the
+    reference's running value (properties are readable at any time)"""
+    rng = np.random.default_rng(11)
+    ch = 2
+    ref, test = synth_pair(41, 14000, ch)
+    o = H.OraclePeaq(advanced, 92.0, ch)
+    p = G.Peaq(0, advanced=advanced, console_output=False)
+    p.set_caps(ch)
+    pos = 0
+    k = 0
+    while pos < ref.size:
+        a = ch * int(rng.integers(50, 900))
+        cr, ct = ref[pos:pos + a], test[pos:pos + a]
+        p.chain_ref(cr)
+        p.chain_test(ct)
+        o.push(cr, ct)
+        pos += a
+        k += 1
+        if k % 7 == 0:
+            mid, want = p.result(), o.result()
+            if want["frames_fft"] or want["frames_fb"]:
+                assert mid["frames_fft"] == want["frames_fft"] and mid["frames_fb"] == want["frames_fb"]
+                np.testing.assert_allclose(mid["movs"], want["movs"], rtol=MOV_RTOL, atol=1e-9, equal_nan=True)
+    res = p.stop()
+    o.finish()
+    want = o.result()
+    np.testing.assert_allclose(res["movs"], want["movs"], rtol=MOV_RTOL, atol=1e-9, equal_nan=True)
+    assert res["frames_fft"] == want["frames_fft"] and res["frames_fb"] == want["frames_fb"]
+    p.close()
