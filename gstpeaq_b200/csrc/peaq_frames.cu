@@ -222,40 +222,51 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
   }
   __syncwarp();
   // upward spreading (:664-671): source band i adds Ene[i] * aUCEe[i]^(j-i) to every
-  // j > i.  Each lane walks its (up to 4) source bands upwards in lock step; at
-  // step t all written targets i+t are distinct, so plain read-modify-write is safe.
-  double r[4], a[4];
+  // j > i.  Lane l owns sources AND targets l + 32 m.  At step t = 32 A + b every lane
+  // advances its sources (r *= a, the only serial chain) and each target fetches the
+  // contribution of source j - t from lane (l - b) mod 32, slot m - A (or m - A - 1 when
+  // the lane index wraps) with a shuffle: no shared memory, no barrier in the loop.
+  double r[4], a[4], acc[4];
 #pragma unroll
   for (int m = 0; m < 4; m++) {
     const int i = lane + 32 * m;
     r[m] = i < B ? se[i] : 0.;
     a[m] = i < B ? sa[i] : 0.;
+    acc[m] = i < B ? se2[i] : 0.;
   }
-  // slot m (sources lane + 32 m) only reaches targets below B for t < B - 32 m:
-  // run the step loop in four ranges with 4, 3, 2, 1 live slots
-  auto ladder = [&](int t_begin, int t_end, auto slots) {
-    constexpr int kSlots = decltype(slots)::value;
-    for (int t = t_begin; t < t_end; t++) {
+  auto ladder = [&](auto range, int b_begin, int b_end) {
+    constexpr int A = decltype(range)::value;   // t = 32 A + b
+    for (int b = b_begin; b < b_end; b++) {
+      const int src = (lane - b) & 31;
+      const bool same = lane >= b;
+      double v[4 - A];
 #pragma unroll
-      for (int m = 0; m < kSlots; m++) {
-        const int j = lane + 32 * m + t;
-        if (j < B) {
-          r[m] *= a[m];
-          se2[j] += r[m];
-        }
+      for (int m = 0; m < 4 - A; m++) {
+        r[m] *= a[m];
+        v[m] = __shfl_sync(0xffffffffu, r[m], src);
       }
-      __syncwarp();
+#pragma unroll
+      for (int mt = A; mt < 4; mt++) {
+        const double lo = mt - A - 1 >= 0 ? v[mt - A - 1 >= 0 ? mt - A - 1 : 0] : 0.;
+        acc[mt] += same ? v[mt - A] : lo;
+      }
     }
   };
-  const int e3 = B - 96 > 1 ? B - 96 : 1, e2 = B - 64 > 1 ? B - 64 : 1, e1 = B - 32 > 1 ? B - 32 : 1;
-  ladder(1, e3, std::integral_constant<int, 4>());
-  ladder(e3, e2, std::integral_constant<int, 3>());
-  ladder(e2, e1, std::integral_constant<int, 2>());
-  ladder(e1, B, std::integral_constant<int, 1>());
+  {
+    const int last = B - 1;   // largest step
+    ladder(std::integral_constant<int, 0>(), 1, last < 31 ? last + 1 : 32);
+    if (last >= 32) ladder(std::integral_constant<int, 1>(), 0, last < 63 ? last - 31 : 32);
+    if (last >= 64) ladder(std::integral_constant<int, 2>(), 0, last < 95 ? last - 63 : 32);
+    if (last >= 96) ladder(std::integral_constant<int, 3>(), 0, last - 95);
+  }
   // E2 = E2s^(1/0.4) / norm  (:673-675); x^2.5 = x^2 sqrt(x)
-  for (int i = lane; i < B; i += 32) {
-    const double v = se2[i];
-    out[i] = v * v * sqrt(v) / T->spread_norm[i];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const int i = lane + 32 * m;
+    if (i < B) {
+      const double v = acc[m];
+      out[i] = v * v * sqrt(v) / T->spread_norm[i];
+    }
   }
 }
 
