@@ -146,6 +146,7 @@ struct FftPasses {
 // recursion ends once LQ reaches 4^(LOG2N/2)
 template <int NT, typename Sync> struct FftPasses<10, 1024, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
 template <int NT, typename Sync> struct FftPasses<9, 256, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
+template <int NT, typename Sync> struct FftPasses<7, 64, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
 template <int NT, typename Sync> struct FftPasses<8, 256, NT, Sync> { static __device__ __forceinline__ void run(double2*, const double2*, int, Sync) {} };
 
 // Forward transform (kernel exp(-2 pi i k n / N)) by NT threads.  `tw` =

@@ -273,14 +273,19 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
 // Error harmonic structure of one channel (peaq_mov_ehs, movs.c:1383-1441),
 // run by one warp.  d[0..511] = ln(Pw_test/Pw_ref) is in `dlog` (shared).
 // work: 2048 doubles of warp-private shared memory.
+//
+// Transform sizes are halved wherever a sequence is real:
+//   - both forward transforms of do_xcorr (movs.c:1300-1303) are packed into ONE
+//     512-point complex FFT (real part d[0..511], imaginary part d[0..255] | 0);
+//   - the inverse of the Hermitian product (movs.c:1304-1313) is a 256-point complex
+//     FFT of the even/odd recombined spectrum;
+//   - the final 256-point real transform (movs.c:1428) is a 128-point complex FFT.
 __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* dlog, double* work,
                               const double2* __restrict__ tw, int lane) {
   double2* za = reinterpret_cast<double2*>(work);         // 512 complex
-  double2* zb = reinterpret_cast<double2*>(work) + 512;   // 512 complex
+  double2* zb = reinterpret_cast<double2*>(work) + 512;   // 256 complex (+ 129 doubles of |C|^2)
   const int sl9 = fft_slot_rt<9>(lane);
-  const int sw = fft_swz(lane);
-  // both forward transforms of do_xcorr (movs.c:1300-1303) in one complex FFT:
-  // real part = d[0..511], imaginary part = d[0..255] followed by zeros
+  const int sl8 = fft_slot_rt<8>(lane);
 #pragma unroll
   for (int u = 0; u < 16; u++) {
     const double v = dlog[lane + 32 * u];
@@ -288,25 +293,41 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
   }
   __syncwarp();
   warp_fft<9>(za, tw, lane);
-  // F1 = (Z[k] + conj Z[N-k]) / 2, F2 = (Z[k] - conj Z[N-k]) / 2i,
-  // G = F1 * conj(F2) / 512 (movs.c:1304-1312); store conj(G) for the inverse
+  // G[q] = F1[q] conj(F2[q]) / 512 with F1 = (Z[q] + conj Z[-q]) / 2, F2 = (Z[q] - conj Z[-q]) / 2i
+  auto g_of = [&](int q) {
+    const double2 p = za[fft_swz(q & 511)];
+    const double2 m = za[fft_swz((512 - q) & 511)];
+    const double f1r = 0.5 * (p.x + m.x), f1i = 0.5 * (p.y - m.y);
+    const double f2r = 0.5 * (p.y + m.y), f2i = -0.5 * (p.x - m.x);
+    return make_double2((f1r * f2r + f1i * f2i) / (2 * kMaxLag), (f2r * f1i - f1r * f2i) / (2 * kMaxLag));
+  };
+  // real inverse of length 512 through a 256-point complex transform: with
+  // E = G[k] + conj G[256-k], O = (G[k] - conj G[256-k]) e^{+2 pi i k / 512}, Z' = E + i O,
+  // c[2m] + i c[2m+1] = sum_k Z'[k] e^{+2 pi i k m / 256} = conj FFT(conj Z')[m]
 #pragma unroll
-  for (int u = 0; u < 16; u++) {
+  for (int u = 0; u < 8; u++) {
     const int k = lane + 32 * u;
-    const double2 p = za[sw ^ fft_swz(32 * u)];
-    const double2 q = za[fft_swz((512 - k) & 511)];
-    const double f1r = 0.5 * (p.x + q.x), f1i = 0.5 * (p.y - q.y);
-    const double f2r = 0.5 * (p.y + q.y), f2i = -0.5 * (p.x - q.x);
-    const double gr = (f1r * f2r + f1i * f2i) / (2 * kMaxLag);
-    const double gi = (f2r * f1i - f1r * f2i) / (2 * kMaxLag);
-    zb[sl9 ^ fft_slot<9>(32 * u)] = make_double2(gr, -gi);
+    const double2 a = g_of(k), b = g_of(256 - k);
+    const double er = a.x + b.x, ei = a.y - b.y;
+    const double dr = a.x - b.x, di = a.y + b.y;
+    const double2 w = tw[2 * k];                      // e^{-2 pi i k / 512}; its conjugate is needed
+    const double orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+    zb[sl8 ^ fft_slot<8>(32 * u)] = make_double2(er - oi, -(ei + orr));   // conj(E + i O)
   }
   __syncwarp();
-  warp_fft<9>(zb, tw, lane);   // c[l] = Re zb[l]  (unnormalised inverse, like GstFFT)
+  warp_fft<8>(zb, tw, lane);
+  // lane owns lags i = 8*lane .. 8*lane+7: c[2m] = Re, c[2m+1] = -Im of element m = 4*lane + p
+  double c[8];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const double2 v = zb[fft_swz(4 * lane + p)];
+    c[2 * p] = v.x;
+    c[2 * p + 1] = -v.y;
+  }
   // normalisation by the running window energy (movs.c:1405-1418):
   //   c[i] /= sqrt(d0 * dk_i),  dk_i = d0 + sum_{j<i} (d[j+256]^2 - d[j]^2)
-  const double d0 = zb[fft_swz(0)].x;
-  double term[8], c[8];   // lane owns i = 8*lane .. 8*lane+7
+  const double d0 = __shfl_sync(0xffffffffu, c[0], 0);
+  double term[8];
   double local = 0.;
 #pragma unroll
   for (int e = 0; e < 8; e++) {
@@ -327,28 +348,39 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
   double csum = 0.;
 #pragma unroll
   for (int e = 0; e < 8; e++) {
-    const int i = 8 * lane + e;
-    c[e] = zb[fft_swz(i)].x / sqrt(d0 * dk);
+    c[e] = c[e] / sqrt(d0 * dk);
     csum += c[e];
     dk += term[e];
   }
   const double cavg = warp_sum(csum) / kMaxLag;
   __syncwarp();
-  // subtract mean, window (movs.c:1419-1421), 256-pt real FFT as a complex one
+  // subtract mean, window (movs.c:1419-1421); 256 real points as 128 complex ones
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
-    const int i = 8 * lane + e;
-    za[fft_slot_rt<8>(i)] = make_double2((c[e] - cavg) * T->ehs_window[i], 0.);
+  for (int p = 0; p < 4; p++) {
+    const int i = 8 * lane + 2 * p;
+    za[fft_slot_rt<7>(4 * lane + p)] =
+        make_double2((c[2 * p] - cavg) * T->ehs_window[i], (c[2 * p + 1] - cavg) * T->ehs_window[i + 1]);
   }
   __syncwarp();
-  warp_fft<8>(za, tw, lane);
+  warp_fft<7>(za, tw, lane);
+  // C[k] = E + e^{-2 pi i k / 256} O,  k = 0..128;  |C[k]|^2 into shared memory
+  double* s2 = reinterpret_cast<double*>(zb);
+  for (int k = lane; k <= kMaxLag / 2; k += 32) {
+    const double2 p = za[fft_swz(k & 127)];
+    const double2 m = za[fft_swz((128 - k) & 127)];
+    const double er = 0.5 * (p.x + m.x), ei = 0.5 * (p.y - m.y);
+    const double orr = 0.5 * (p.y + m.y), oi = -0.5 * (p.x - m.x);
+    const double2 w = fft_tw(tw, 4 * k);
+    const double xr = er + (orr * w.x - oi * w.y);
+    const double xi = ei + (orr * w.y + oi * w.x);
+    s2[k] = xr * xr + xi * xi;
+  }
+  __syncwarp();
   // largest |C[k]|^2 among 1 <= k <= 128 that rises above its left neighbour
   // (movs.c:1433-1440; NaNs never win a comparison, exactly as there)
   double best = 0.;
   for (int k = 1 + lane; k <= kMaxLag / 2; k += 32) {
-    const double2 x = za[fft_swz(k)], y = za[fft_swz(k - 1)];
-    const double s = x.x * x.x + x.y * x.y;
-    const double sp = y.x * y.x + y.y * y.y;
+    const double s = s2[k], sp = s2[k - 1];
     if (s > sp && s > best) best = s;
   }
   return warp_max_nonan(best);
