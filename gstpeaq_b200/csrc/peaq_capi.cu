@@ -146,13 +146,15 @@ struct Engine {
   size_t hp_state_cap = 0;
   double* d_fbout = nullptr;
   size_t fbout_cap = 0;
+  double* d_fbenergy = nullptr;   // rectified sub-step energies [stream][sub-step][band]
+  size_t fbenergy_cap = 0;
   unsigned char* d_fbflags = nullptr;
   size_t fbflags_cap = 0;
   double* d_fbdbg = nullptr;
   size_t fbdbg_cap = 0;
   size_t last_fbdbg_doubles = 0;
   unsigned last_fb_frames = 0;
-  size_t fb_budget_bytes = (size_t)24 << 30;
+  size_t fb_budget_bytes = (size_t)32 << 30;
   float* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [slot][ref|test]
   size_t stage_cap[2] = {0, 0};   // floats, per buffer of the slot
   cudaStream_t copy_stream = nullptr;
@@ -214,6 +216,7 @@ struct Engine {
     cudaFree(d_hp);
     cudaFree(d_hp_state);
     cudaFree(d_fbout);
+    cudaFree(d_fbenergy);
     cudaFree(d_fbflags);
     cudaFree(d_fbdbg);
     cudaFree(d_tables);
@@ -412,7 +415,7 @@ struct Engine {
       }
       // ---- filter-bank clock: chunks of 192-sample frames -----------------------
       const int n_streams = n_pairs * 2 * C;
-      const size_t per_frame = (size_t)n_streams * (kFbFrame * sizeof(double) + 6 * kFbBands * 2 * sizeof(double));
+      const size_t per_frame = (size_t)n_streams * (kFbFrame * sizeof(double) + 6 * kFbBands * 3 * sizeof(double));
       size_t chunk = std::max<unsigned>(max_fb_frames, 1);
       if (chunk * per_frame > fb_budget_bytes) {
         chunk = std::max<size_t>(fb_budget_bytes / per_frame, 8);
@@ -426,6 +429,7 @@ struct Engine {
         return fail(PEAQ_B200_ERR_INVALID, "filter state would be lost on growth");
       if ((rc = ensure(&d_hp_state, &hp_state_cap, (size_t)n_streams * kHpStateDoubles))) return rc;
       if ((rc = ensure(&d_fbout, &fbout_cap, (size_t)n_streams * kFbBands * chunk * 6 * 2))) return rc;
+      if ((rc = ensure(&d_fbenergy, &fbenergy_cap, (size_t)n_streams * kFbBands * chunk * 6))) return rc;
       if ((rc = ensure(&d_fbflags, &fbflags_cap, (size_t)n_pairs * chunk))) return rc;
       double* dbg = nullptr;
       last_fbdbg_doubles = 0;
@@ -446,15 +450,17 @@ struct Engine {
         PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
                                hp_stride, d_hp_state, first == 0 && reset_state, stream));
         PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, stream));
-        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbout, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,
+        PEAQ_CUDA(launch_fb_spread(d_tables, d_fbout, n_sub, pcm_fb.n_frames, first, d_state, A, d_fbenergy,
+                                   n_pairs, stream));
+        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,
                                  dbg, n_pairs, stream));
-        launches += 4;
+        launches += 5;
         if ((rc = timer_end())) return rc;
         first += n;
       }
       if (max_fb_frames == 0 && reset_state) {
         // publish the (empty) fb-clock MOVs so the epilogue sees 0/0 like the reference
-        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbout, 0, d_fbflags, pcm_fb.n_frames, 0, 0, d_state, A, nullptr,
+        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, 0, d_fbflags, pcm_fb.n_frames, 0, 0, d_state, A, nullptr,
                                  n_pairs, stream));
         launches++;
       }

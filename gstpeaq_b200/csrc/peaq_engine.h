@@ -77,12 +77,12 @@ struct AdvStateLayout {
   int off_fft_filtered;   // [c][55]            time smearing of the ref excitation
   int off_fft_acc;        // [c][2][kAccFields] SegmentalNMR, EHS
   int off_fft_scalar;     // signal / noise energy
-  int off_fb_stream;      // [2C streams][cu 40 | excitation 40 | history 11 x 40]
+  int off_fb_stream;      // [2C streams][cu 40 | excitation 40 | last sub-step energies, newest first, 11 x 40 (5 used)]
   int off_fb_level;       // [c][6][40]
   int off_fb_mod;         // [c][ref|test][3][40]
   int off_fb_acc;         // [c][3][kAccFields] RmsModDiff, RmsNoiseLoudAsym, AvgLinDist
   int off_fb_movs;        // 3 channel-averaged MOV values published by the fb scan
-  int off_ints;           // int32: fft status, fft frames, fb status, fb frames, loudness frame, history slot
+  int off_ints;           // int32: fft status, fft frames, fb status, fb frames, loudness frame, (unused)
   int stride;
 };
 
@@ -159,7 +159,10 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
                            const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
                            double* fbout, cudaStream_t stream);
 cudaError_t launch_init_adv_state(double* state, AdvStateLayout S, int n_pairs, cudaStream_t stream);
-cudaError_t launch_fb_scan(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
+cudaError_t launch_fb_spread(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
+                             const unsigned* n_frames, unsigned first_frame, double* state,
+                             AdvStateLayout S, double* energy, int n_pairs, cudaStream_t stream);
+cudaError_t launch_fb_scan(const DeviceTables* d_tables, const double* energy, unsigned n_sub,
                            const unsigned char* flags, const unsigned* n_frames, unsigned first_frame,
                            unsigned n_chunk_frames, double* state, AdvStateLayout S, double* dbg,
                            int n_pairs, cudaStream_t stream);

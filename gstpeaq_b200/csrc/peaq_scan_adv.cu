@@ -1,12 +1,18 @@
 // Advanced-mode recurrent kernels.
 //
-// FB3 `fb_scan_kernel`: back half of the filter-bank ear model and everything
-// that runs on the 192-sample clock.  One CTA per pair, one warp per stream
-// (channel, ref|test), lane = band (40 bands: lane l owns band l and, for l < 8,
-// band 32 + l).  Per 32-sample sub-step (fbearmodel.c:320-369): level dependent
-// slope with its first-order smoothing `cu`, upward spreading as 39 lock-step
-// shared-memory steps, downward spreading, rectification, 11-deep history.  Per
-// frame (6 sub-steps): backward-masking FIR, internal noise, forward masking
+// FB3a `fb_spread_kernel`: frequency-domain spreading and rectification of the
+// filter-bank outputs (fbearmodel.c:320-357), once per 32-sample sub-step.  Only the
+// first-order smoothing of the slope `cu` carries state from one sub-step to the next;
+// everything else is independent per sub-step, so a CTA (one per stream) works on tiles
+// of 32 sub-steps: the level-dependent slope of every (band, sub-step) in parallel, the
+// 40 `cu` recurrences serially through the tile, then one thread per (sub-step, re|im)
+// runs the upward ladder entirely in registers -- in the reference's own order, source
+// band by source band, so the sums round exactly as there -- and the downward pass.
+//
+// FB3b `fb_scan_kernel`: everything that runs on the 192-sample clock.  One CTA per
+// pair, one warp per stream (channel, ref|test), lane = band (40 bands: lane l owns band
+// l and, for l < 8, band 32 + l).  Per frame: backward-masking FIR over the last eleven
+// sub-step energies (kept in registers), internal noise, forward masking
 // (fbearmodel.c:371-395); then per channel (the ref warp): level / pattern
 // adaptation and modulation at 40 bands (leveladapter.c, modpatt.c), loudness
 // latch, RmsModDiffA, RmsNoiseLoudAsymA, AvgLinDistA with their accumulators
@@ -55,7 +61,6 @@ enum { kCFc, kCNoise, kCNoise03, kCAEar, kCAProc, kCEthres, kCThres, kCLoudfac, 
 
 struct FbSmem {
   double cst[kCCount][kFbBands];
-  double hist[2 * kMaxChannels][11][kFbBands];
   double ex_u[2 * kMaxChannels][kFbBands];
   double ex_e[2 * kMaxChannels][kFbBands];
   double lv[kMaxChannels][6][kFbBands];       // ref_filt, test_filt, num, den, pc_ref, pc_test
@@ -65,8 +70,110 @@ struct FbSmem {
   int latch;
 };
 
+constexpr int kSpTile = 32;   // sub-steps per tile
+constexpr int kSpPad = 33;    // row pitch: column reads (fixed sub-step) and row-major read-out both conflict free
+
+struct SpreadSmem {
+  double re[kFbBands][kSpPad];
+  double im[kFbBands][kSpPad];
+  double cu[kFbBands][kSpPad];   // DIST^s, then the smoothed slope
+  double slope0[kFbBands];       // 24 + 230 / fc
+};
+
+__global__ void __launch_bounds__(2 * kSpTile, 6)
+fb_spread_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ fbout, unsigned n_sub,
+                 const unsigned* __restrict__ n_frames, unsigned first_frame, double* __restrict__ state,
+                 AdvStateLayout S, double* __restrict__ energy /* [stream][n_sub][40] */) {
+  __shared__ SpreadSmem sm;
+  const int stream = blockIdx.x;
+  const int per_pair = 2 * S.C;
+  const int pair = stream / per_pair;
+  double* st_stream = state + (size_t)pair * S.stride + S.off_fb_stream + (stream % per_pair) * (2 + 11) * kFbBands;
+  const unsigned total = n_frames[pair];
+  const unsigned valid = total > first_frame ? min((total - first_frame) * 6u, n_sub) : 0u;
+  const int tid = threadIdx.x, t = tid & 31, part = tid >> 5;
+  double cu_state = 0.;
+  if (tid < kFbBands) {
+    cu_state = st_stream[tid];
+    sm.slope0[tid] = 24 + 230 / T->fb.fc[tid];
+  }
+  const double2* __restrict__ my_out = fbout + (size_t)stream * kFbBands * n_sub;
+  double* __restrict__ my_e = energy + (size_t)stream * kFbBands * n_sub;
+  __syncthreads();
+
+  for (unsigned s0 = 0; s0 < valid; s0 += kSpTile) {
+    const int nt = (int)min((unsigned)kSpTile, valid - s0);
+    // ---- level dependent slope of every (band, sub-step) (fbearmodel.c:326-331) ----
+    if (t < nt) {
+#pragma unroll 4
+      for (int k = 0; k < kFbBands / 2; k++) {
+        const int b = part + 2 * k;
+        const double2 o = my_out[(size_t)b * n_sub + s0 + t];
+        const double L = 10 * log10(o.x * o.x + o.y * o.y);
+        const double slope = sm.slope0[b] - 0.2 * L;
+        const double sl_eff = 4 > slope ? 4 : slope;      // MAX (4, ...)
+        sm.re[b][t] = o.x;
+        sm.im[b][t] = o.y;
+        sm.cu[b][t] = exp(sl_eff * kLnDist);               // DIST^s
+      }
+    }
+    __syncthreads();
+    // ---- first-order smoothing along time, one thread per band (fbearmodel.c:336) ----
+    if (tid < kFbBands) {
+      for (int i = 0; i < nt; i++) {
+        cu_state = cu_state + kSlopeA * (sm.cu[tid][i] - cu_state);
+        sm.cu[tid][i] = cu_state;
+      }
+    }
+    __syncthreads();
+    // ---- spreading of one sub-step, real or imaginary part, in registers ------------
+    if (t < nt) {
+      double* xs = part ? &sm.im[0][t] : &sm.re[0][t];
+      const double* cs = &sm.cu[0][t];
+      double A[kFbBands];
+#pragma unroll
+      for (int j = 0; j < kFbBands; j++) A[j] = xs[j * kSpPad];
+      // upward (fbearmodel.c:337-347): source b adds out[b] cu[b]^(j-b) to every j > b;
+      // eight sources advance together so that their multiply chains overlap
+#pragma unroll
+      for (int g = 0; g < kFbBands; g += 8) {
+        double r[8], c[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          r[q] = xs[(g + q) * kSpPad];
+          c[q] = cs[(g + q) * kSpPad];
+        }
+#pragma unroll
+        for (int j = g + 1; j < kFbBands; j++) {
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            if (g + q < j) {
+              r[q] *= c[q];
+              A[j] += r[q];
+            }
+          }
+        }
+      }
+      // downward with the constant slope CL (fbearmodel.c:350-353)
+#pragma unroll
+      for (int j = kFbBands - 1; j > 0; j--) A[j - 1] += kCl * A[j];
+#pragma unroll
+      for (int j = 0; j < kFbBands; j++) xs[j * kSpPad] = A[j];
+    }
+    __syncthreads();
+    // ---- rectification (fbearmodel.c:356-359); [sub-step][band] rows are contiguous ----
+    for (int e = tid; e < nt * kFbBands; e += 2 * kSpTile) {
+      const int i = e / kFbBands, b = e - i * kFbBands;
+      const double ar = sm.re[b][i], ai = sm.im[b][i];
+      my_e[(size_t)s0 * kFbBands + e] = ar * ar + ai * ai;
+    }
+    __syncthreads();
+  }
+  if (tid < kFbBands) st_stream[tid] = cu_state;
+}
+
 __global__ void __launch_bounds__(64 * kMaxChannels, 4)
-fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ fbout,
+fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ energy,
                unsigned n_sub /* sub-steps per stream in this chunk */,
                const unsigned char* __restrict__ flags, const unsigned* __restrict__ n_frames,
                unsigned first_frame, unsigned n_chunk_frames, double* __restrict__ state,
@@ -81,16 +188,18 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
   int* st_ints = reinterpret_cast<int*>(st + S.off_ints);
 
   // ---- load state and constants -----------------------------------------------
-  double cu[2], exc[2];
+  // exc: forward-masked excitation; prev: the five sub-step energies before the
+  // current frame, oldest first (the state keeps them newest first)
+  double exc[2], prev[2][5];
   double* st_stream = st + S.off_fb_stream + warp * (2 + 11) * kFbBands;
 #pragma unroll
   for (int sl = 0; sl < 2; sl++) {
     const int b = lane + 32 * sl;
     const bool ok = b < kFbBands;
-    cu[sl] = ok ? st_stream[b] : 0.;
     exc[sl] = ok ? st_stream[kFbBands + b] : 0.;
+#pragma unroll
+    for (int k = 0; k < 5; k++) prev[sl][4 - k] = ok ? st_stream[(2 + k) * kFbBands + b] : 0.;
     if (ok) {
-      for (int i = 0; i < 11; i++) sm.hist[warp][i][b] = st_stream[(2 + i) * kFbBands + b];
       if (side == 0) {
         for (int f = 0; f < 6; f++) sm.lv[chan][f][b] = st[S.off_fb_level + (chan * 6 + f) * kFbBands + b];
         for (int sd = 0; sd < 2; sd++)
@@ -114,126 +223,44 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
   int status = st_ints[2];
   unsigned frame_counter = (unsigned)st_ints[3];
   unsigned loud_frame = (unsigned)st_ints[4];
-  int pos = st_ints[5];          // slot of the newest history entry
   __syncthreads();
 
   const double deriv_factor = (double)48000 / kFbFrame;
-  double cl_to_32 = 1.;   // CL^(32 - lane)
-  for (int i = lane; i < 32; i++) cl_to_32 *= kCl;
-  const double2* __restrict__ my_out = fbout + (size_t)stream * kFbBands * n_sub;
+  const double* __restrict__ my_e = energy + (size_t)stream * kFbBands * n_sub;
+  double bm[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) bm[i] = T->fb_back_mask[i];
 
   const unsigned total = n_frames[pair];
   const unsigned end = min(first_frame + n_chunk_frames, total);
+  // the six sub-step energies of a frame, loaded one frame ahead
+  double cur[2][6];
+  auto load_frame = [&](unsigned fl, double (&dst)[2][6]) {
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++) {
+      const int b = lane + 32 * sl;
+#pragma unroll
+      for (int sub = 0; sub < 6; sub++)
+        dst[sl][sub] = b < kFbBands ? my_e[((size_t)fl * 6 + sub) * kFbBands + b] : 0.;
+    }
+  };
+  if (first_frame < end) load_frame(0, cur);
   for (unsigned f = first_frame; f < end; f++) {
     const unsigned fl = f - first_frame;
     const bool above = flags[(size_t)pair * n_chunk_frames + fl] != 0;
     if (threadIdx.x == 0) sm.latch = 0;   // set after the first barrier, read after the second
-    // ---- six sub-steps of the ear model (fbearmodel.c:314-369) ----------------
-    for (int sub = 0; sub < 6; sub++) {
-      const unsigned s = fl * 6 + sub;
-      // out[band] of this sub-step; lane l holds band l (slot 0) and band 32 + l (slot 1, l < 8)
-      double d1[2], d2[2], are[2], aim[2];
-#pragma unroll
-      for (int sl = 0; sl < 2; sl++) {
-        const int b = lane + 32 * sl;
-        d1[sl] = d2[sl] = 0.;
-        if (b < kFbBands) {
-          const double2 o = my_out[(size_t)b * n_sub + s];
-          const double L = 10 * log10(o.x * o.x + o.y * o.y);
-          const double slope = 24 + 230 / sm.cst[kCFc][b] - 0.2 * L;
-          const double sl_eff = 4 > slope ? 4 : slope;      // MAX (4, ...), fbearmodel.c:329
-          const double dist_s = exp(sl_eff * kLnDist);       // DIST^s
-          cu[sl] = cu[sl] + kSlopeA * (dist_s - cu[sl]);
-          d1[sl] = o.x;
-          d2[sl] = o.y;
-        }
-        are[sl] = d1[sl];
-        aim[sl] = d2[sl];
-      }
-      // upward spreading (fbearmodel.c:339-348): source band b adds out[b] * cu[b]^k to
-      // band b + k.  Each lane advances its own sources (d *= cu); the target lane
-      // fetches step k's contribution from lane - k with a shuffle, wrapping from
-      // slot-0 sources (bands 32+l-k) into the slot-1 targets -- no shared memory,
-      // no barrier, the only serial chain is the multiply.
-      for (int k = 1; k < kFbBands; k++) {
-        d1[0] *= cu[0];
-        d2[0] *= cu[0];
-        const int src = (lane - k) & 31;
-        const double v0r = __shfl_sync(0xffffffffu, d1[0], src);
-        const double v0i = __shfl_sync(0xffffffffu, d2[0], src);
-        if (lane >= k) {            // slot-0 target `lane` from slot-0 source lane - k
-          are[0] += v0r;
-          aim[0] += v0i;
-        } else if (lane < 8 && k <= 32 + lane) {   // slot-1 target 32+lane from slot-0 source 32+lane-k
-          are[1] += v0r;
-          aim[1] += v0i;
-        }
-        if (k < 8) {                // slot-1 sources only reach slot-1 targets, k <= 7
-          d1[1] *= cu[1];
-          d2[1] *= cu[1];
-          const double v1r = __shfl_sync(0xffffffffu, d1[1], src);
-          const double v1i = __shfl_sync(0xffffffffu, d2[1], src);
-          if (lane >= k && lane < 8) {
-            are[1] += v1r;
-            aim[1] += v1i;
-          }
-        }
-      }
-      // downward spreading with the constant slope CL (fbearmodel.c:351-354):
-      // A[b] = sum_{j >= b} CL^(j-b) A[j], as shuffle scans (slot 1 first, its total
-      // enters slot 0 through band 32)
-      {
-        double q = kCl;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {     // bands 32..39 live in lanes 0..7
-          const double ur = __shfl_down_sync(0xffffffffu, are[1], o);
-          const double ui = __shfl_down_sync(0xffffffffu, aim[1], o);
-          if (lane + o < 8) {
-            are[1] = are[1] + q * ur;
-            aim[1] = aim[1] + q * ui;
-          }
-          q = q * q;
-        }
-        const double hr = __shfl_sync(0xffffffffu, are[1], 0);   // A[32] after the scan
-        const double hi = __shfl_sync(0xffffffffu, aim[1], 0);
-        q = kCl;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double ur = __shfl_down_sync(0xffffffffu, are[0], o);
-          const double ui = __shfl_down_sync(0xffffffffu, aim[0], o);
-          if (lane + o < 32) {
-            are[0] = are[0] + q * ur;
-            aim[0] = aim[0] + q * ui;
-          }
-          q = q * q;
-        }
-        are[0] = are[0] + cl_to_32 * hr;    // CL^(32 - lane) * A[32]
-        aim[0] = aim[0] + cl_to_32 * hi;
-      }
-      // rectification + history (fbearmodel.c:357-368)
-      pos = pos == 10 ? 0 : pos + 1;
-#pragma unroll
-      for (int sl = 0; sl < 2; sl++) {
-        const int b = lane + 32 * sl;
-        if (b < kFbBands) sm.hist[warp][pos][b] = are[sl] * are[sl] + aim[sl] * aim[sl];
-      }
-      __syncwarp();
-    }
+    double nxt[2][6];
+    if (f + 1 < end) load_frame(fl + 1, nxt);
     // ---- backward masking, noise, forward masking (fbearmodel.c:371-395) -------
+    // E0_buf[i] (i = 0 newest) is cur[5 - i] for i <= 5 and prev[10 - i] beyond
 #pragma unroll
     for (int sl = 0; sl < 2; sl++) {
       const int b = lane + 32 * sl;
       if (b < kFbBands) {
         double e1 = 0.;
-        for (int i = 0; i < 5; i++) {
-          const int pa_ = pos - i < 0 ? pos - i + 11 : pos - i;
-          const int pb_ = pos - (10 - i) < 0 ? pos - (10 - i) + 11 : pos - (10 - i);
-          e1 += (sm.hist[warp][pa_][b] + sm.hist[warp][pb_][b]) * T->fb_back_mask[i];
-        }
-        {
-          const int pc_ = pos - 5 < 0 ? pos - 5 + 11 : pos - 5;
-          e1 += sm.hist[warp][pc_][b] * T->fb_back_mask[5];
-        }
+#pragma unroll
+        for (int i = 0; i < 5; i++) e1 += (cur[sl][5 - i] + prev[sl][i]) * bm[i];
+        e1 += cur[sl][0] * bm[5];
         const double U = e1 + sm.cst[kCNoise][b];
         const double a_ear = sm.cst[kCAEar][b];
         exc[sl] = a_ear * exc[sl] + (1. - a_ear) * U;
@@ -246,6 +273,10 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
           d[kFbBands + b] = exc[sl];
         }
       }
+#pragma unroll
+      for (int k = 0; k < 5; k++) prev[sl][k] = cur[sl][k + 1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cur[sl][k] = nxt[sl][k];
     }
     __syncthreads();   // excitations of all streams visible
 
@@ -461,9 +492,9 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
   for (int sl = 0; sl < 2; sl++) {
     const int b = lane + 32 * sl;
     if (b < kFbBands) {
-      st_stream[b] = cu[sl];
       st_stream[kFbBands + b] = exc[sl];
-      for (int i = 0; i < 11; i++) st_stream[(2 + i) * kFbBands + b] = sm.hist[warp][i][b];
+#pragma unroll
+      for (int k = 0; k < 5; k++) st_stream[(2 + k) * kFbBands + b] = prev[sl][4 - k];
       if (side == 0) {
         for (int f = 0; f < 6; f++) st[S.off_fb_level + (chan * 6 + f) * kFbBands + b] = sm.lv[chan][f][b];
         for (int sd = 0; sd < 2; sd++)
@@ -479,7 +510,6 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__ f
     st_ints[2] = status;
     st_ints[3] = (int)frame_counter;
     st_ints[4] = (int)loud_frame;
-    st_ints[5] = pos;
     // peaq_movaccum_get_value (movaccum.c:438-481), averaged over channels
     const bool tent = status == kStTentative;
     double v0 = 0., v1 = 0., v2 = 0.;
@@ -630,7 +660,7 @@ __global__ void init_adv_state_kernel(double* state, AdvStateLayout S, int n_pai
     if (o == S.off_ints + 2) {
       int* ints = reinterpret_cast<int*>(state + i);
       ints[0] = (int)UINT_MAX;   // slot 4: loudness_reached_frame
-      ints[1] = 10;              // slot 5: newest history entry (next write goes to 0)
+      ints[1] = 0;
     } else {
       state[i] = 0.;
     }
@@ -647,14 +677,22 @@ cudaError_t launch_init_adv_state(double* state, AdvStateLayout S, int n_pairs, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_fb_scan(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
+cudaError_t launch_fb_spread(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
+                             const unsigned* n_frames, unsigned first_frame, double* state,
+                             AdvStateLayout S, double* energy, int n_pairs, cudaStream_t stream) {
+  if (n_pairs <= 0 || n_sub == 0) return cudaSuccess;
+  fb_spread_kernel<<<n_pairs * 2 * S.C, 2 * kSpTile, 0, stream>>>(
+      d_tables, reinterpret_cast<const double2*>(fbout), n_sub, n_frames, first_frame, state, S, energy);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fb_scan(const DeviceTables* d_tables, const double* energy, unsigned n_sub,
                            const unsigned char* flags, const unsigned* n_frames, unsigned first_frame,
                            unsigned n_chunk_frames, double* state, AdvStateLayout S, double* dbg,
                            int n_pairs, cudaStream_t stream) {
   if (n_pairs <= 0) return cudaSuccess;
-  fb_scan_kernel<<<n_pairs, 64 * S.C, 0, stream>>>(d_tables, reinterpret_cast<const double2*>(fbout), n_sub,
-                                                    flags, n_frames, first_frame, n_chunk_frames, state, S,
-                                                    dbg);
+  fb_scan_kernel<<<n_pairs, 64 * S.C, 0, stream>>>(d_tables, energy, n_sub, flags, n_frames, first_frame,
+                                                    n_chunk_frames, state, S, dbg);
   return cudaGetLastError();
 }
 
