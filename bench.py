@@ -34,6 +34,8 @@ N_SAMPLES = 48000 * PAIR_SECONDS
 CHANNELS = 2
 PAIRS_PER_GPU = 4096
 BYTES_PER_FRAME = 1024 * CHANNELS * 4 * 2        # algorithmic HBM read per PEAQ frame
+# CPU arm: pairs per host core and step (basic: ~3 s of work per core, advanced ~20 s)
+CPU_PAIRS_PER_CORE = 12
 METRIC = "48 kHz stereo PEAQ frames/sec"
 UNIT = "frames/s"
 
@@ -102,7 +104,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_pairs = max(cores, min(PAIRS_PER_GPU, cores * 2))
+    n_pairs = max(cores, min(PAIRS_PER_GPU, cores * CPU_PAIRS_PER_CORE))
     times = []
     frames = 0
     kind = cpu_kind()
@@ -349,7 +351,7 @@ def our_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = max(cores, min(PAIRS_PER_GPU, cores * 2))
+        n_cpu = max(cores, min(PAIRS_PER_GPU, cores * CPU_PAIRS_PER_CORE))
         fps, fr, busy, wall, kind = run_cpu_sample(n_cpu, cores)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "first %d of %d pairs x %d s, one process per core, %.1f s wall" % (n_cpu, PAIRS_PER_GPU, PAIR_SECONDS, wall)}

@@ -419,8 +419,10 @@ struct Engine {
       size_t chunk = std::max<unsigned>(max_fb_frames, 1);
       if (chunk * per_frame > fb_budget_bytes) {
         chunk = std::max<size_t>(fb_budget_bytes / per_frame, 8);
-        // 112 frames = 672 sub-steps = 3 FIR tiles of 224: no partially filled tiles
-        if (chunk >= 112) chunk -= chunk % 112;
+        // 224 frames = 1344 sub-steps = 6 direct-FIR tiles of 224 = 7 recursion tiles of 192:
+        // no partially filled tiles
+        if (chunk >= 224) chunk -= chunk % 224;
+        else if (chunk >= 32) chunk -= chunk % 32;
       }
       if (keep_records) chunk = std::max<unsigned>(max_fb_frames, 1);
       const size_t hp_stride = kFbHist + chunk * kFbFrame;
@@ -449,7 +451,11 @@ struct Engine {
         PEAQ_CUDA(launch_fb_flags(pcm_fb, n_pairs, first, n, d_fbflags, stream));
         PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
                                hp_stride, d_hp_state, first == 0 && reset_state, stream));
-        PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, stream));
+        // PEAQ_B200_FB_DIRECT=1: all 40 filters as direct FIRs (development aid / cross-check)
+        static const bool fb_direct = std::getenv("PEAQ_B200_FB_DIRECT") && std::atoi(std::getenv("PEAQ_B200_FB_DIRECT"));
+        PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, d_hp_state,
+                                 first == 0 && reset_state, fb_direct, stream));
+        if (!fb_direct) launches++;
         PEAQ_CUDA(launch_fb_spread(d_tables, d_fbout, n_sub, pcm_fb.n_frames, first, d_state, A, d_fbenergy,
                                    n_pairs, stream));
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,

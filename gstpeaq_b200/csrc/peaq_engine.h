@@ -21,7 +21,7 @@ constexpr int kMaxChannels = 2;
 constexpr int kNumAcc = 11;        // accumulator slots (11 basic MOVs; 5 used in advanced)
 constexpr int kAccFields = 8;      // num, den, x0, x1, x2, saved num, saved den, saved max
 constexpr int kBandStateFields = 14;
-constexpr int kHpStateDoubles = 6 + kFbHist;   // DC-reject filter state + FIR history per stream (even: 16-byte rows)
+constexpr int kHpStateDoubles = 6 + kFbHist + 2 * 3 * kFbRecBands;   // DC-reject filter state + FIR history per stream (even: 16-byte rows)
 
 // Layout of one per-frame record written by K1 and read by K2 (units: doubles).
 struct RecordLayout {
@@ -157,7 +157,8 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
                          cudaStream_t stream);
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
                            const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
-                           double* fbout, cudaStream_t stream);
+                           double* fbout, double* hp_state, bool first_chunk, bool direct_only,
+                           cudaStream_t stream);
 cudaError_t launch_init_adv_state(double* state, AdvStateLayout S, int n_pairs, cudaStream_t stream);
 cudaError_t launch_fb_spread(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
                              const unsigned* n_frames, unsigned first_frame, double* state,

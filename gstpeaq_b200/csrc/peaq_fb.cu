@@ -269,6 +269,188 @@ fb_bank_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// FB2r: the 26 long filters (N >= 214; 93 % of all taps) as sliding windowed DFTs.
+//
+// Every tap set is a raised-cosine window times a complex exponential
+// (fbearmodel.c:213-220): h[n] = (Wt/N) (2 - e^{j d n} - e^{-j d n}) e^{j w (n - N/2)},
+// d = 2 pi / N.  So the output is the sum of three rectangular-window sums
+//   S_f[s] = g_f sum_{n<N} e^{j w_f n} x[32 s - D - n],   w_f = w, w + d, w - d,
+// and each of those obeys a one-step recursion in the sub-step index s:
+//   S_f[s] = r_f S_f[s-1] + W_f[s],   r_f = e^{j 32 w_f},
+//   W_f[s] = sum_{k<32} P_f[k] x[32 s - D - k] + Q_f[k] x[32 s - D - k - N]
+// (the 32 samples that entered the window and the 32 that left it).  That is
+// 384 FMAs per band and sub-step whatever N is, against 2 (N - 1) for the direct
+// form (2910 for the longest band): 3 x fewer FMAs for the whole bank.
+//
+// One CTA per stream walks through the chunk in tiles of 192 sub-steps; warp w
+// owns bands w, w + 7, w + 14 (, w + 21).  Lane j owns one group of six consecutive
+// sub-steps (one 192-sample frame): it computes W for them from the staged,
+// polyphase-transposed input tile, turns them into the group's zero-state
+// response P_j[i] = sum_{l<=i} r^{i-l} W[6 j + l]; lanes 0-2 (one per frequency)
+// then chain the group totals sequentially, c_j = r^6 c_{j-1} + P_j[5], and
+// every lane finishes with S[6 j + i] = r^{i+1} c_{j-1} + P_j[i].  Groups are
+// anchored at absolute frame boundaries and chunks are whole frames, so the
+// arithmetic of every output is the same however the item is cut into chunks;
+// the chain value (3 complex per band) is the only state carried over.
+// Rounding differs from the direct form at the 1e-14 level relative to the
+// in-window signal (tests/test_gpu_parity.py compares both with the oracle).
+constexpr int kRecTile = 32 * kFbRecGroup;       // 192 sub-steps
+constexpr int kRecHistRows = 47;                 // 1488 samples of history / 32, rounded up
+constexpr int kRecRows = kRecTile + kRecHistRows;
+constexpr int kRecStride = 241;                  // odd multiple of 16 plus one: conflict-free transposing store
+constexpr int kRecWarps = 7;                     // 26 bands: 4,4,4,4,4,3,3 (14 warps per SM: 4 per scheduler, 128 registers)
+constexpr int kRecSlots = 4;
+
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {   // a * b + c
+  return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+__global__ void __launch_bounds__(32 * kRecWarps, 2)
+fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp, size_t hp_stride,
+                   unsigned n_sub /* sub-steps in this chunk, a multiple of 6 */, double2* __restrict__ fbout,
+                   size_t out_stream_stride /* = 40 * n_sub */, double* __restrict__ hp_state,
+                   int first_chunk) {
+  extern __shared__ __align__(16) double xs[];   // [32][kRecStride], then the warps' exchange buffers
+  const int stream = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2* xch = reinterpret_cast<double2*>(xs + 32 * kRecStride) + warp * 96;   // [3][32]
+  const double* __restrict__ src = hp + (size_t)stream * hp_stride + kFbHist;
+  double2* carry_state = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + 6 + kFbHist);
+  const int n_slots = warp + (kRecSlots - 1) * kRecWarps < kFbRecBands ? kRecSlots : kRecSlots - 1;
+  // chain values of this warp's bands: [slot][frequency], kept in shared memory between tiles
+  double2* cst = reinterpret_cast<double2*>(xs + 32 * kRecStride) + kRecWarps * 96 + warp * (3 * kRecSlots);
+  if (lane < 3 * kRecSlots) {
+    const int slot = lane / 3, f = lane - 3 * slot;
+    cst[lane] = (!first_chunk && slot < n_slots) ? carry_state[(warp + kRecWarps * slot) * 3 + f] : make_double2(0., 0.);
+  }
+  __syncwarp();
+  const int n_tiles = (int)((n_sub + kRecTile - 1) / kRecTile);
+  for (int tile = 0; tile < n_tiles; tile++) {
+    const int S0 = tile * kRecTile;
+    const int mbase = S0 - kRecHistRows;
+    __syncthreads();   // the previous tile has been consumed
+    for (int i = threadIdx.x; i < kRecRows * 32; i += blockDim.x) {
+      const int t = mbase * 32 + i;          // chunk-local sample index (>= -kFbHist)
+      const int p = i & 31, mm = i >> 5;
+      xs[p * kRecStride + mm] = t < (int)(n_sub * 32) ? src[t] : 0.;
+    }
+    __syncthreads();
+    const int n_groups = min(32, (int)(n_sub - S0) / kFbRecGroup);
+    const double* __restrict__ col0 = xs + kFbRecGroup * lane + kRecHistRows;   // column of x[32 s0 - 0]
+    for (int slot = 0; slot < n_slots; slot++) {
+      const int b = warp + kRecWarps * slot;
+      const int N = T->fb_len[b];
+      const int D = 1 + (kFbBuf - N) / 2;
+      const double2* __restrict__ ph = reinterpret_cast<const double2*>(&T->fb_rec_ph[b][0][0]);
+      double2 acc[3][kFbRecGroup];
+#pragma unroll
+      for (int f = 0; f < 3; f++)
+#pragma unroll
+        for (int i = 0; i < kFbRecGroup; i++) acc[f][i] = make_double2(0., 0.);
+#pragma unroll 2
+      for (int k = 0; k < 32; k++) {
+        // x[32 s - a] sits in row (-a) mod 32, column s - ceil(a / 32) - mbase
+        {
+          const int a = D + k;
+          const double* __restrict__ px = col0 + ((-a) & 31) * kRecStride - ((a + 31) >> 5);
+          const double2 c0 = __ldg(ph + 6 * k), c1 = __ldg(ph + 6 * k + 1), c2 = __ldg(ph + 6 * k + 2);
+          double x[kFbRecGroup];
+#pragma unroll
+          for (int i = 0; i < kFbRecGroup; i++) x[i] = px[i];
+#pragma unroll
+          for (int i = 0; i < kFbRecGroup; i++) {
+            acc[0][i].x = fma(c0.x, x[i], acc[0][i].x);
+            acc[0][i].y = fma(c0.y, x[i], acc[0][i].y);
+            acc[1][i].x = fma(c1.x, x[i], acc[1][i].x);
+            acc[1][i].y = fma(c1.y, x[i], acc[1][i].y);
+            acc[2][i].x = fma(c2.x, x[i], acc[2][i].x);
+            acc[2][i].y = fma(c2.y, x[i], acc[2][i].y);
+          }
+        }
+        {
+          const int a = D + k + N;
+          const double* __restrict__ px = col0 + ((-a) & 31) * kRecStride - ((a + 31) >> 5);
+          const double2 c0 = __ldg(ph + 6 * k + 3), c1 = __ldg(ph + 6 * k + 4), c2 = __ldg(ph + 6 * k + 5);
+          double x[kFbRecGroup];
+#pragma unroll
+          for (int i = 0; i < kFbRecGroup; i++) x[i] = px[i];
+#pragma unroll
+          for (int i = 0; i < kFbRecGroup; i++) {
+            acc[0][i].x = fma(c0.x, x[i], acc[0][i].x);
+            acc[0][i].y = fma(c0.y, x[i], acc[0][i].y);
+            acc[1][i].x = fma(c1.x, x[i], acc[1][i].x);
+            acc[1][i].y = fma(c1.y, x[i], acc[1][i].y);
+            acc[2][i].x = fma(c2.x, x[i], acc[2][i].x);
+            acc[2][i].y = fma(c2.y, x[i], acc[2][i].y);
+          }
+        }
+      }
+      // zero-state response of the group, P[i] = r P[i-1] + W[i]; group totals to the chain lanes
+      const double2* __restrict__ rp = reinterpret_cast<const double2*>(&T->fb_rec_rpow[b][0][0]);
+#pragma unroll
+      for (int f = 0; f < 3; f++) {
+        const double2 r1 = __ldg(rp + f * kFbRecGroup);
+#pragma unroll
+        for (int i = 1; i < kFbRecGroup; i++) acc[f][i] = cfma(r1, acc[f][i - 1], acc[f][i]);
+        xch[f * 32 + lane] = acc[f][kFbRecGroup - 1];
+      }
+      __syncwarp();
+      if (lane < 3) {
+        const double2 r6 = __ldg(rp + lane * kFbRecGroup + kFbRecGroup - 1);
+        double2 c = cst[3 * slot + lane];
+        double2 tot = xch[lane * 32];
+        for (int j = 0; j < n_groups; j++) {
+          const double2 nxt = xch[lane * 32 + ((j + 1) & 31)];   // fetched ahead of the dependent chain
+          xch[lane * 32 + j] = c;                                // chain value in front of group j
+          c = cfma(r6, c, tot);
+          tot = nxt;
+        }
+        cst[3 * slot + lane] = c;
+      }
+      __syncwarp();
+      double2 out[kFbRecGroup];
+#pragma unroll
+      for (int i = 0; i < kFbRecGroup; i++) out[i] = make_double2(0., 0.);
+#pragma unroll
+      for (int f = 0; f < 3; f++) {
+        const double2 cin = xch[f * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < kFbRecGroup; i++) {
+          const double2 sv = cfma(__ldg(rp + f * kFbRecGroup + i), cin, acc[f][i]);
+          out[i].x += sv.x;
+          out[i].y += sv.y;
+        }
+      }
+      __syncwarp();   // xch is reused by the next band
+      if (b == 0) {
+        // the reference's ring buffer holds 1456 samples, so band 0's last tap (delay 1456)
+        // reads the newest sample instead (fbearmodel.c:311-313,413)
+        const double2 g = make_double2(T->fb_rec_alias.x, T->fb_rec_alias.y);
+        const double* __restrict__ pn = col0;                                              // x[32 s]
+        const double* __restrict__ po = col0 + ((-kFbBuf) & 31) * kRecStride - ((kFbBuf + 31) >> 5);   // x[32 s - 1456]
+#pragma unroll
+        for (int i = 0; i < kFbRecGroup; i++) {
+          const double dx = pn[i] - po[i];
+          out[i].x = fma(g.x, dx, out[i].x);
+          out[i].y = fma(g.y, dx, out[i].y);
+        }
+      }
+      if (lane < n_groups) {
+        double2* __restrict__ o = fbout + (size_t)stream * out_stream_stride + (size_t)b * n_sub + S0 + kFbRecGroup * lane;
+#pragma unroll
+        for (int i = 0; i < kFbRecGroup; i++) o[i] = out[i];
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < 3 * n_slots) {
+    const int slot = lane / 3, f = lane - 3 * slot;
+    carry_state[(warp + kRecWarps * slot) * 3 + f] = cst[lane];
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsigned n_chunk_frames,
@@ -310,8 +492,21 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
 
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
                            const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
-                           double* fbout, cudaStream_t stream) {
+                           double* fbout, double* hp_state, bool first_chunk, bool direct_only,
+                           cudaStream_t stream) {
   if (n_streams <= 0 || n_sub == 0) return cudaSuccess;
+  // long filters through the recursion, the short ones (and, on request, all) directly
+  const int first_band = direct_only ? 0 : kFbRecBands;
+  if (!direct_only) {
+    const size_t smem_rec = sizeof(double) * 32 * kRecStride + sizeof(double2) * (96 + 3 * kRecSlots) * kRecWarps;
+    cudaError_t e = cudaFuncSetAttribute(fb_bank_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+    if (e != cudaSuccess) return e;
+    fb_bank_rec_kernel<<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
+        d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
+        first_chunk ? 1 : 0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   // distribute the 40 bands over the warps, longest filters first, always onto
   // the least loaded warp
   BankBands bb;
@@ -319,7 +514,7 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
   int count[kBankWarps] = {0};
   for (int w = 0; w < kBankWarps; w++)
     for (int s = 0; s < 8; s++) bb.band[w][s] = -1;
-  for (int b = 0; b < kFbBands; b++) {   // lengths are sorted descending already
+  for (int b = first_band; b < kFbBands; b++) {   // lengths are sorted descending already
     int best = 0;
     for (int w = 1; w < kBankWarps; w++)
       if (load[w] < load[best]) best = w;

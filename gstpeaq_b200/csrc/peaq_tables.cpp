@@ -198,6 +198,39 @@ void fill_fb_model(DeviceTables* t, double playback_level) {
     }
     g += local;
   }
+  // recursive form of the long filters; phases in long double so that what a sample adds
+  // when it enters the window is what gets removed N samples later (to ~1e-19)
+  for (int band = 0; band < kFbRecBands; band++) {
+    const int N = kFbLen[band];
+    const long double pi = 3.141592653589793238462643383279502884L;
+    const long double w = 2 * pi * (long double)fc[band] / 48000.L;
+    const long double d = 2 * pi / N;
+    const long double wf[3] = {w, w + d, w - d};
+    const long double gain[3] = {2.L, -1.L, -1.L};
+    const long double amp = (long double)ear_weight(fc[band]) / N;
+    for (int f = 0; f < 3; f++) {
+      for (int k = 0; k < 32; k++) {
+        // g_f e^{j w_f k} with g_f = gain_f amp e^{-j w N / 2}
+        const long double a = wf[f] * k - w * N / 2;
+        t->fb_rec_ph[band][k][f].x = (double)(gain[f] * amp * cosl(a));
+        t->fb_rec_ph[band][k][f].y = (double)(gain[f] * amp * sinl(a));
+        const long double a2 = a + w * N;   // times -e^{j w N}
+        t->fb_rec_ph[band][k][3 + f].x = (double)(-gain[f] * amp * cosl(a2));
+        t->fb_rec_ph[band][k][3 + f].y = (double)(-gain[f] * amp * sinl(a2));
+      }
+      for (int i = 0; i < kFbRecGroup; i++) {
+        t->fb_rec_rpow[band][f][i].x = (double)cosl(32 * wf[f] * (i + 1));
+        t->fb_rec_rpow[band][f][i].y = (double)sinl(32 * wf[f] * (i + 1));
+      }
+    }
+  }
+  {
+    // band 0, n = N - 1 (delay 1456): same expression as the tap table above
+    const double* hre = t->fb_h_re + t->fb_tap_offset[0];
+    const double* him = t->fb_h_im + t->fb_tap_offset[0];
+    t->fb_rec_alias.x = hre[1];
+    t->fb_rec_alias.y = -him[1];
+  }
   for (int i = 0; i < 6; i++)
     t->fb_back_mask[i] =
         std::cos(M_PI * (i - 5.) / 12.) * std::cos(M_PI * (i - 5.) / 12.) * 0.9761 / 6.;

@@ -20,6 +20,8 @@ constexpr int kMaxLag = 256;       // movs.c:42
 constexpr int kFbTapsTotal = 10954; // sum over bands of (N/2+1), N from Table 8 of BS.1387
 constexpr int kFbHist = 1504;      // filtered samples kept in front of a chunk (>= 1456 + 32, multiple of 32)
 constexpr int kFbGTotal = 21868;   // sum over bands of the delay support length (N-1, band 0: N)
+constexpr int kFbRecBands = 26;    // bands 0..25 (N >= 214) run as sliding windowed DFTs, the rest as direct FIRs
+constexpr int kFbRecGroup = 6;     // sub-steps per recursion group (= one 192-sample frame)
 
 struct double2_t { double x, y; };
 
@@ -77,6 +79,16 @@ struct DeviceTables {
   int fb_g_offset[kFbBands];
   int fb_phase_offset[kFbBands * 32];
   alignas(16) double fb_g[2 * kFbGTotal];
+  // Long filters as recursions (see fb_bank_rec_kernel).  The taps are a raised-cosine
+  // window times a complex exponential (fbearmodel.c:213-220), so with w = 2 pi fc / 48000,
+  // d = 2 pi / N, w_f = {w, w + d, w - d}, g_f = {2, -1, -1} (Wt / N) e^{-j w N / 2}
+  //   out[s] = sum_f S_f[s],   S_f[s] = g_f sum_{n < N} e^{j w_f n} x[32 s - D - n]
+  //   S_f[s] = e^{j 32 w_f} S_f[s-1] + sum_{k < 32} (P_f[k] x[32 s - D - k] + Q_f[k] x[32 s - D - k - N])
+  // fb_rec_ph[b][k] = {P_0, P_+, P_-, Q_0, Q_+, Q_-}[k], P_f[k] = g_f e^{j w_f k}, Q_f[k] = -e^{j w N} P_f[k];
+  // fb_rec_rpow[b][f][i] = e^{j 32 w_f (i + 1)}, i < 6
+  alignas(16) double2_t fb_rec_ph[kFbRecBands][32][6];
+  alignas(16) double2_t fb_rec_rpow[kFbRecBands][3][kFbRecGroup];
+  double2_t fb_rec_alias;           // band 0: tap at delay 1456, which the reference reads from the newest sample
   // neural network (nn.c:40-93)
   double nn_amin[11], nn_amax[11];
   double nn_wx[11 * 5];             // [input][hidden], row stride 5
