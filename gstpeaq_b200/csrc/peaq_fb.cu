@@ -271,7 +271,7 @@ fb_bank_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp
 
 
 // ---------------------------------------------------------------------------
-// FB2r: the 26 long filters (N >= 214; 93 % of all taps) as sliding windowed DFTs.
+// FB2r: the filter bank as sliding windowed DFTs.
 //
 // Every tap set is a raised-cosine window times a complex exponential
 // (fbearmodel.c:213-220): h[n] = (Wt/N) (2 - e^{j d n} - e^{-j d n}) e^{j w (n - N/2)},
@@ -282,10 +282,13 @@ fb_bank_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp
 //   W_f[s] = sum_{k<32} P_f[k] x[32 s - D - k] + Q_f[k] x[32 s - D - k - N]
 // (the 32 samples that entered the window and the 32 that left it).  That is
 // 384 FMAs per band and sub-step whatever N is, against 2 (N - 1) for the direct
-// form (2910 for the longest band): 3 x fewer FMAs for the whole bank.
+// form (2910 for the longest band, 102 for the shortest): 15.4 k instead of 43.6 k
+// FMAs per sub-step for the whole bank.  (Keeping the twelve shortest filters
+// direct would save another 3 k FMAs; a fused direct pass for them was measured
+// slower because of its constant-operand traffic and is not kept.)
 //
 // One CTA per stream walks through the chunk in tiles of 192 sub-steps; warp w
-// owns bands w, w + 7, w + 14 (, w + 21).  Lane j owns one group of six consecutive
+// owns bands w, w + 8, ..., w + 32.  Lane j owns one group of six consecutive
 // sub-steps (one 192-sample frame): it computes W for them from the staged,
 // polyphase-transposed input tile, turns them into the group's zero-state
 // response P_j[i] = sum_{l<=i} r^{i-l} W[6 j + l]; lanes 0-2 (one per frequency)
@@ -299,12 +302,79 @@ fb_bank_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp
 constexpr int kRecTile = 32 * kFbRecGroup;       // 192 sub-steps
 constexpr int kRecHistRows = 47;                 // 1488 samples of history / 32, rounded up
 constexpr int kRecRows = kRecTile + kRecHistRows;
-constexpr int kRecStride = 241;                  // odd multiple of 16 plus one: conflict-free transposing store
-constexpr int kRecWarps = 7;                     // 26 bands: 4,4,4,4,4,3,3 (14 warps per SM: 4 per scheduler, 128 registers)
-constexpr int kRecSlots = 4;
+constexpr int kRecStride = 242;                  // even: the six columns of a lane keep their 16-byte alignment from row to row
+constexpr int kRecWarps = 8;                     // 40 bands, 5 per warp (16 warps per SM: 4 per scheduler, 128 registers)
+constexpr int kRecSlots = 5;
+constexpr int kRecXsDoubles = 32 * kRecStride + 4;   // input tile incl. padding at both ends (even)
 
 __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {   // a * b + c
   return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+
+// six consecutive doubles px[0..5] with 128-bit shared loads.  Lanes are 48 bytes apart, so
+// every quarter-warp hits eight distinct 16-byte bank groups (64-bit loads at this stride
+// would conflict two-way).  kOdd: px is 8 mod 16 (the same for all lanes of the warp).
+template <bool kOdd>
+__device__ __forceinline__ void load6(const double* __restrict__ px, double (&x)[6]) {
+  if (!kOdd) {
+    const double2 v0 = *reinterpret_cast<const double2*>(px);
+    const double2 v1 = *reinterpret_cast<const double2*>(px + 2);
+    const double2 v2 = *reinterpret_cast<const double2*>(px + 4);
+    x[0] = v0.x; x[1] = v0.y; x[2] = v1.x; x[3] = v1.y; x[4] = v2.x; x[5] = v2.y;
+  } else {
+    const double2 v0 = *reinterpret_cast<const double2*>(px - 1);
+    const double2 v1 = *reinterpret_cast<const double2*>(px + 1);
+    const double2 v2 = *reinterpret_cast<const double2*>(px + 3);
+    const double2 v3 = *reinterpret_cast<const double2*>(px + 5);
+    x[0] = v0.y; x[1] = v1.x; x[2] = v1.y; x[3] = v2.x; x[4] = v2.y; x[5] = v3.x;
+  }
+}
+
+// acc[f][i] += coef[3 k + f] * px[i] for k in [k0, k1), px moving up one row (one sample
+// back in time) per k
+template <bool kOdd>
+__device__ __forceinline__ void rec_accumulate(double2 (&acc)[3][kFbRecGroup], const double* __restrict__ px,
+                                               const double2* __restrict__ coef, int k0, int k1) {
+#pragma unroll 2
+  for (int k = k0; k < k1; k++) {
+    double x[kFbRecGroup];
+    load6<kOdd>(px, x);
+    const double2 c0 = coef[3 * k], c1 = coef[3 * k + 1], c2 = coef[3 * k + 2];
+#pragma unroll
+    for (int i = 0; i < kFbRecGroup; i++) {
+      acc[0][i].x = fma(c0.x, x[i], acc[0][i].x);
+      acc[0][i].y = fma(c0.y, x[i], acc[0][i].y);
+      acc[1][i].x = fma(c1.x, x[i], acc[1][i].x);
+      acc[1][i].y = fma(c1.y, x[i], acc[1][i].y);
+      acc[2][i].x = fma(c2.x, x[i], acc[2][i].x);
+      acc[2][i].y = fma(c2.y, x[i], acc[2][i].y);
+    }
+    px -= kRecStride;
+  }
+}
+
+// the 32 samples x[32 s - a0 - k], k < 32, of the lane's six sub-steps against coef[3 k + f].
+// x[32 s - a] sits in row (-a) mod 32, column s - ceil(a / 32) - mbase: the row falls by one
+// per k and wraps once, where the column steps back and (the row pitch being even) the
+// 16-byte alignment of the lane's six columns flips.
+__device__ __forceinline__ void rec_side(double2 (&acc)[3][kFbRecGroup], const double* __restrict__ col0, int a0,
+                                         const double2* __restrict__ coef) {
+  const int row = (-a0) & 31, q = (a0 + 31) >> 5;
+  const int k1 = row + 1;   // k < k1: before the wrap
+  const double* __restrict__ px = col0 + row * kRecStride - q;
+  if (reinterpret_cast<uintptr_t>(px) & 8) {
+    rec_accumulate<true>(acc, px, coef, 0, k1);
+    rec_accumulate<false>(acc, col0 + 31 * kRecStride - (q + 1), coef, k1, 32);
+  } else {
+    rec_accumulate<false>(acc, px, coef, 0, k1);
+    rec_accumulate<true>(acc, col0 + 31 * kRecStride - (q + 1), coef, k1, 32);
+  }
+}
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(32 * kRecWarps, 2)
@@ -312,81 +382,70 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
                    unsigned n_sub /* sub-steps in this chunk, a multiple of 6 */, double2* __restrict__ fbout,
                    size_t out_stream_stride /* = 40 * n_sub */, double* __restrict__ hp_state,
                    int first_chunk) {
-  extern __shared__ __align__(16) double xs[];   // [32][kRecStride], then the warps' exchange buffers
+  extern __shared__ __align__(16) double xs_raw[];   // 2 doubles of padding, [32][kRecStride], then the warps' buffers
+  double* xs = xs_raw + 2;                            // (a misaligned 128-bit load may start one double early)
   const int stream = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double2* xch = reinterpret_cast<double2*>(xs + 32 * kRecStride) + warp * 96;   // [3][32]
+  double2* xch = reinterpret_cast<double2*>(xs_raw + kRecXsDoubles) + warp * 96;   // [3][32]
   const double* __restrict__ src = hp + (size_t)stream * hp_stride + kFbHist;
   double2* carry_state = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + 6 + kFbHist);
   const int n_slots = warp + (kRecSlots - 1) * kRecWarps < kFbRecBands ? kRecSlots : kRecSlots - 1;
   // chain values of this warp's bands: [slot][frequency], kept in shared memory between tiles
-  double2* cst = reinterpret_cast<double2*>(xs + 32 * kRecStride) + kRecWarps * 96 + warp * (3 * kRecSlots);
+  double2* cst = reinterpret_cast<double2*>(xs_raw + kRecXsDoubles) + kRecWarps * 96 + warp * (3 * kRecSlots);
+  // this warp's copy of the current band's coefficient table (global loads of it kept
+  // missing L1 behind the streaming input tile)
+  double2* phs = reinterpret_cast<double2*>(xs_raw + kRecXsDoubles) + kRecWarps * (96 + 3 * kRecSlots) + warp * 192;
   if (lane < 3 * kRecSlots) {
     const int slot = lane / 3, f = lane - 3 * slot;
     cst[lane] = (!first_chunk && slot < n_slots) ? carry_state[(warp + kRecWarps * slot) * 3 + f] : make_double2(0., 0.);
   }
   __syncwarp();
   const int n_tiles = (int)((n_sub + kRecTile - 1) / kRecTile);
+  const int t_end = (int)(n_sub * 32);
   for (int tile = 0; tile < n_tiles; tile++) {
     const int S0 = tile * kRecTile;
     const int mbase = S0 - kRecHistRows;
     __syncthreads();   // the previous tile has been consumed
+    // polyphase-transposed tile through asynchronous 8-byte copies: all of a thread's loads
+    // are in flight together
     for (int i = threadIdx.x; i < kRecRows * 32; i += blockDim.x) {
       const int t = mbase * 32 + i;          // chunk-local sample index (>= -kFbHist)
       const int p = i & 31, mm = i >> 5;
-      xs[p * kRecStride + mm] = t < (int)(n_sub * 32) ? src[t] : 0.;
+      if (t < t_end) cp_async8(&xs[p * kRecStride + mm], src + t);
+      else xs[p * kRecStride + mm] = 0.;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    // the next tile's new samples towards L2 while this one is being worked on
+    {
+      const int t_next = (S0 + kRecTile) * 32 + threadIdx.x * 16;   // 128-byte lines
+      for (int t = t_next; t < (S0 + 2 * kRecTile) * 32 && t < t_end; t += blockDim.x * 16)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + t));
+    }
     const int n_groups = min(32, (int)(n_sub - S0) / kFbRecGroup);
     const double* __restrict__ col0 = xs + kFbRecGroup * lane + kRecHistRows;   // column of x[32 s0 - 0]
     for (int slot = 0; slot < n_slots; slot++) {
       const int b = warp + kRecWarps * slot;
       const int N = T->fb_len[b];
       const int D = 1 + (kFbBuf - N) / 2;
-      const double2* __restrict__ ph = reinterpret_cast<const double2*>(&T->fb_rec_ph[b][0][0]);
+      {
+        const double2* __restrict__ ph = reinterpret_cast<const double2*>(&T->fb_rec_ph[b][0][0]);
+        // [side][k][f] in shared memory
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          const int e = lane + 32 * u;          // = 6 k + side * 3 + f
+          const int k = e / 6, r = e - 6 * k;
+          phs[(r >= 3 ? 96 : 0) + 3 * k + (r >= 3 ? r - 3 : r)] = __ldg(ph + e);
+        }
+        __syncwarp();
+      }
       double2 acc[3][kFbRecGroup];
 #pragma unroll
       for (int f = 0; f < 3; f++)
 #pragma unroll
         for (int i = 0; i < kFbRecGroup; i++) acc[f][i] = make_double2(0., 0.);
-#pragma unroll 2
-      for (int k = 0; k < 32; k++) {
-        // x[32 s - a] sits in row (-a) mod 32, column s - ceil(a / 32) - mbase
-        {
-          const int a = D + k;
-          const double* __restrict__ px = col0 + ((-a) & 31) * kRecStride - ((a + 31) >> 5);
-          const double2 c0 = __ldg(ph + 6 * k), c1 = __ldg(ph + 6 * k + 1), c2 = __ldg(ph + 6 * k + 2);
-          double x[kFbRecGroup];
-#pragma unroll
-          for (int i = 0; i < kFbRecGroup; i++) x[i] = px[i];
-#pragma unroll
-          for (int i = 0; i < kFbRecGroup; i++) {
-            acc[0][i].x = fma(c0.x, x[i], acc[0][i].x);
-            acc[0][i].y = fma(c0.y, x[i], acc[0][i].y);
-            acc[1][i].x = fma(c1.x, x[i], acc[1][i].x);
-            acc[1][i].y = fma(c1.y, x[i], acc[1][i].y);
-            acc[2][i].x = fma(c2.x, x[i], acc[2][i].x);
-            acc[2][i].y = fma(c2.y, x[i], acc[2][i].y);
-          }
-        }
-        {
-          const int a = D + k + N;
-          const double* __restrict__ px = col0 + ((-a) & 31) * kRecStride - ((a + 31) >> 5);
-          const double2 c0 = __ldg(ph + 6 * k + 3), c1 = __ldg(ph + 6 * k + 4), c2 = __ldg(ph + 6 * k + 5);
-          double x[kFbRecGroup];
-#pragma unroll
-          for (int i = 0; i < kFbRecGroup; i++) x[i] = px[i];
-#pragma unroll
-          for (int i = 0; i < kFbRecGroup; i++) {
-            acc[0][i].x = fma(c0.x, x[i], acc[0][i].x);
-            acc[0][i].y = fma(c0.y, x[i], acc[0][i].y);
-            acc[1][i].x = fma(c1.x, x[i], acc[1][i].x);
-            acc[1][i].y = fma(c1.y, x[i], acc[1][i].y);
-            acc[2][i].x = fma(c2.x, x[i], acc[2][i].x);
-            acc[2][i].y = fma(c2.y, x[i], acc[2][i].y);
-          }
-        }
-      }
+      rec_side(acc, col0, D, phs);            // the 32 samples that entered the window
+      rec_side(acc, col0, D + N, phs + 96);   // the 32 that left it
       // zero-state response of the group, P[i] = r P[i-1] + W[i]; group totals to the chain lanes
       const double2* __restrict__ rp = reinterpret_cast<const double2*>(&T->fb_rec_rpow[b][0][0]);
 #pragma unroll
@@ -423,7 +482,7 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
           out[i].y += sv.y;
         }
       }
-      __syncwarp();   // xch is reused by the next band
+      __syncwarp();   // xch and phs are reused by the next band
       if (b == 0) {
         // the reference's ring buffer holds 1456 samples, so band 0's last tap (delay 1456)
         // reads the newest sample instead (fbearmodel.c:311-313,413)
@@ -495,17 +554,17 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
                            double* fbout, double* hp_state, bool first_chunk, bool direct_only,
                            cudaStream_t stream) {
   if (n_streams <= 0 || n_sub == 0) return cudaSuccess;
-  // long filters through the recursion, the short ones (and, on request, all) directly
-  const int first_band = direct_only ? 0 : kFbRecBands;
+  // default: all filters through the recursion (fb_bank_rec_kernel); direct_only: all 40 as
+  // polyphase direct FIRs (cross-check)
   if (!direct_only) {
-    const size_t smem_rec = sizeof(double) * 32 * kRecStride + sizeof(double2) * (96 + 3 * kRecSlots) * kRecWarps;
-    cudaError_t e = cudaFuncSetAttribute(fb_bank_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+    cudaError_t e;
+    const size_t smem_rec = sizeof(double) * kRecXsDoubles + sizeof(double2) * (96 + 3 * kRecSlots + 192) * kRecWarps;
+    e = cudaFuncSetAttribute(fb_bank_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
     if (e != cudaSuccess) return e;
     fb_bank_rec_kernel<<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
         d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
         first_chunk ? 1 : 0);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
   }
   // distribute the 40 bands over the warps, longest filters first, always onto
   // the least loaded warp
@@ -514,7 +573,7 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
   int count[kBankWarps] = {0};
   for (int w = 0; w < kBankWarps; w++)
     for (int s = 0; s < 8; s++) bb.band[w][s] = -1;
-  for (int b = first_band; b < kFbBands; b++) {   // lengths are sorted descending already
+  for (int b = 0; b < kFbBands; b++) {   // lengths are sorted descending already
     int best = 0;
     for (int w = 1; w < kBankWarps; w++)
       if (load[w] < load[best]) best = w;

@@ -20,7 +20,7 @@ constexpr int kMaxLag = 256;       // movs.c:42
 constexpr int kFbTapsTotal = 10954; // sum over bands of (N/2+1), N from Table 8 of BS.1387
 constexpr int kFbHist = 1504;      // filtered samples kept in front of a chunk (>= 1456 + 32, multiple of 32)
 constexpr int kFbGTotal = 21868;   // sum over bands of the delay support length (N-1, band 0: N)
-constexpr int kFbRecBands = 26;    // bands 0..25 (N >= 214) run as sliding windowed DFTs, the rest as direct FIRs
+constexpr int kFbRecBands = 40;    // all bands run as sliding windowed DFTs (the direct FIR kernel is kept as a cross-check)
 constexpr int kFbRecGroup = 6;     // sub-steps per recursion group (= one 192-sample frame)
 
 struct double2_t { double x, y; };
