@@ -34,10 +34,7 @@ namespace {
 
 constexpr int kWorkDoubles = 2048;   // per-warp buffer: 1024 complex points
 constexpr int kTwDoubles = 2 * 512;
-constexpr int kScratchA = 1032;      // sa  [128]
-constexpr int kScratchE = 1160;      // se  [128]
-constexpr int kScratchE2 = 1288;     // se2 [128]
-constexpr int kScratchDlog = 1536;   // dlog[512] (test warp's buffer)
+constexpr int kScratchDlog = 1536;   // dlog[512] (test stream's buffer)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -61,19 +58,6 @@ __device__ __forceinline__ int warp_max_int(int v) {
     v = x > v ? x : v;
   }
   return v;
-}
-
-// barrier of the two warps (ref, test) of one channel
-__device__ __forceinline__ void channel_barrier(int chan) {
-  asm volatile("bar.sync %0, 64;" ::"r"(chan + 1) : "memory");
-}
-
-// producer / consumer halves of the same barrier (one warp arrives, the other waits)
-__device__ __forceinline__ void channel_arrive(int chan) {
-  asm volatile("bar.arrive %0, 64;" ::"r"(chan + 1 + kMaxChannels) : "memory");
-}
-__device__ __forceinline__ void channel_wait(int chan) {
-  asm volatile("bar.sync %0, 64;" ::"r"(chan + 1 + kMaxChannels) : "memory");
 }
 
 // ---- TMA (cp.async.bulk) staging of one frame of interleaved PCM into shared memory ----
@@ -117,27 +101,21 @@ __device__ __forceinline__ float pcm_at(const float* __restrict__ sig, unsigned 
 }
 
 // literal replay of is_frame_above_threshold for one channel (gstpeaq.c:1088-1096):
-// FLOAT running sum, double increments; only used for borderline frames
-__device__ bool replay_threshold(const float* __restrict__ sig, unsigned long long s0,
-                                 unsigned long long n_samples, int c, int C, int lane) {
-  int result = 0;
-  if (lane == 0) {
-    const double thr = 200. / 32768;
-    float sum = 0;
-    int i;
-    for (i = 0; i < 5; i++)
-      sum = (float)((double)sum + fabs((double)pcm_at(sig, s0, n_samples, i, c, C)));
-    while (i < kFftFrame) {
-      sum = (float)((double)sum + (fabs((double)pcm_at(sig, s0, n_samples, i, c, C)) -
-                                   fabs((double)pcm_at(sig, s0, n_samples, i - 5, c, C))));
-      if ((double)sum >= thr) {
-        result = 1;
-        break;
-      }
-      i++;
-    }
+// FLOAT running sum, double increments; run by one thread, only for borderline frames
+__device__ bool replay_threshold_serial(const float* __restrict__ sig, unsigned long long s0,
+                                        unsigned long long n_samples, int c, int C) {
+  const double thr = 200. / 32768;
+  float sum = 0;
+  int i;
+  for (i = 0; i < 5; i++)
+    sum = (float)((double)sum + fabs((double)pcm_at(sig, s0, n_samples, i, c, C)));
+  while (i < kFftFrame) {
+    sum = (float)((double)sum + (fabs((double)pcm_at(sig, s0, n_samples, i, c, C)) -
+                                 fabs((double)pcm_at(sig, s0, n_samples, i - 5, c, C))));
+    if ((double)sum >= thr) return true;
+    i++;
   }
-  return __shfl_sync(0xffffffffu, result, 0) != 0;
+  return false;
 }
 
 // peaq_fftearmodel_group_into_bands for band i (fftearmodel.c:603-620); `spec`
@@ -386,10 +364,56 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
   return warp_max_nonan(best);
 }
 
-__global__ void __launch_bounds__(128, 3)
+// ---- kernel -------------------------------------------------------------------------------
+// Per-stream buffer (2048 doubles), after the FFT:
+//   [0, 769)      weighted power spectrum, bins 0..768 (nothing reads higher bins: grouping stops
+//                 at 18 kHz = bin 768, the EHS at bin 511; the bandwidth decisions use registers)
+//   test buffer:  [776, 1160) spreading scratch of the test stream, [1536, 2048) ln spectrum ratio
+//   ref buffer:   [1536, 1920) spreading scratch of the ref stream; [0, 1536) is recycled by the
+//                 EHS transforms once every reader of the ref spectrum has arrived
+constexpr int kSpecBins = 769;
+constexpr int kScratchTest = 776;
+constexpr int kScratchRef = 1536;
+
+struct FrameMail {
+  double thr_part[kMaxChannels][2];
+  double snr_s[kMaxChannels][2], snr_n[kMaxChannels][2];
+  double energy[2 * kMaxChannels][2];
+  float maxabs[kMaxChannels][2];
+  int bw_ref_part[kMaxChannels][2];
+  int bw_test_part[kMaxChannels][2];
+  unsigned long long mbar;
+};
+
+// barrier of the two warps of one stream (ids 1..4), of the four warps of one channel
+// (ids 5, 6) and the arrive/wait pair that guards the ref buffer (ids 7, 8)
+struct StreamSync {
+  int id;
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+};
+__device__ __forceinline__ void chan_sync(int chan) {
+  asm volatile("bar.sync %0, 128;" ::"r"(5 + chan) : "memory");
+}
+__device__ __forceinline__ void refbuf_arrive(int chan) {
+  asm volatile("bar.arrive %0, 128;" ::"r"(7 + chan) : "memory");
+}
+__device__ __forceinline__ void refbuf_wait(int chan) {
+  asm volatile("bar.sync %0, 128;" ::"r"(7 + chan) : "memory");
+}
+
+// One CTA = one FFT-clock frame of one pair; 4 C warps.  Two warps share a stream (channel c,
+// side: 0 ref, 1 test) up to the weighted power spectrum -- staging, window, FFT, power
+// spectrum, bandwidth -- so every thread holds 16 bins instead of 32 and a CTA needs half the
+// registers per thread: 24 warps per SM instead of 12 for the same shared memory.  After
+// that the four warps of a channel split into tasks:
+//   ref-h0 : grouping + spreading of the ref stream
+//   ref-h1 : grouping + spreading of the test stream
+//   test-h0: half of the ln spectrum ratio and of the noise bands, then the EHS
+//   test-h1: the other halves
+__global__ void __launch_bounds__(256, 3)
 fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned first_frame,
                   unsigned n_chunk_frames, double* __restrict__ records, RecordLayout L, int B,
-                  int advanced, int debug_stop) {
+                  int advanced) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = pcm.channels;
   const int pair = blockIdx.x / n_chunk_frames;
@@ -399,15 +423,17 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int chan = warp >> 1;
-  const int side = warp & 1;
+  const int stream = warp >> 1;       // 2 * channel + side
+  const int half = warp & 1;
+  const int chan = stream >> 1;
+  const int side = stream & 1;
+  const int t = half * 32 + lane;     // thread within the stream
+  const int role = warp & 3;          // 0 ref-h0, 1 ref-h1, 2 test-h0, 3 test-h1
 
   double* smem = reinterpret_cast<double*>(smem_raw);
   double2* tw = reinterpret_cast<double2*>(smem);                       // 512 complex
-  double* work = smem + kTwDoubles + warp * kWorkDoubles;
-  double* mail = smem + kTwDoubles + 2 * C * kWorkDoubles;              // cross-warp mailbox
-  int* mail_flags = reinterpret_cast<int*>(mail + 8);                   // [2C] energy, [C] above, [C] bw_ref
-  double* mail_thr = mail + 16;                                         // [C]
+  double* work = smem + kTwDoubles + stream * kWorkDoubles;
+  FrameMail* mail = reinterpret_cast<FrameMail*>(smem + kTwDoubles + 2 * C * kWorkDoubles);
 
   for (int i = threadIdx.x; i < 512; i += blockDim.x)
     tw[i] = make_double2(T->tw1024[i].x, T->tw1024[i].y);
@@ -416,37 +442,36 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   const unsigned long long n_sig = side ? n_test : n_ref;
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
   const float* __restrict__ ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
-  const float* __restrict__ sig = side ? pcm.test + (size_t)pair * pcm.pair_stride : ref_sig;
   const float* __restrict__ test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  const float* __restrict__ sig = side ? test_sig : ref_sig;
   // whole frame inside both signals and 16-byte aligned: stage it with two TMA bulk
-  // copies (ref -> warp 0's buffer, test -> warp 1's buffer, both still unused);
+  // copies (ref -> stream 0's buffer, test -> stream 1's buffer, both still unused);
   // otherwise (last, zero-padded frame; odd strides) fall back to guarded scalar loads
-  const bool tma_ok = C <= 2 && (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 &&
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(test_sig) & 15) == 0 &&
                       s0 + kFftFrame <= n_ref && s0 + kFftFrame <= n_test;
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(mail + 24);
   float* raw_ref = reinterpret_cast<float*>(smem + kTwDoubles);
   float* raw_test = reinterpret_cast<float*>(smem + kTwDoubles + kWorkDoubles);
   if (tma_ok) {
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    if (threadIdx.x == 0) mbar_init(&mail->mbar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned bytes = kFftFrame * C * sizeof(float);
-      mbar_expect_tx(mbar, 2 * bytes);
-      tma_load_1d(raw_ref, ref_sig + s0 * C, bytes, mbar);
-      tma_load_1d(raw_test, test_sig + s0 * C, bytes, mbar);
+      mbar_expect_tx(&mail->mbar, 2 * bytes);
+      tma_load_1d(raw_ref, ref_sig + s0 * C, bytes, &mail->mbar);
+      tma_load_1d(raw_test, test_sig + s0 * C, bytes, &mail->mbar);
     }
   }
 
-  // ---- phase 1: this stream's 2048 samples into registers; SNR sums ----------------
-  float xs0[32], xs1[32];
+  // ---- phase 1: this thread's 32 samples (complex points n = t + 64 u) into registers ----
+  float xs0[16], xs1[16];
   double energy = 0., es = 0., en = 0.;
   if (tma_ok) {
-    mbar_wait(mbar, 0);
+    mbar_wait(&mail->mbar, 0);
     const float* raw = side ? raw_test : raw_ref;
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int n = lane + 32 * u;   // complex index: samples 2n, 2n+1
+    for (int u = 0; u < 16; u++) {
+      const int n = t + 64 * u;   // samples 2n, 2n+1
       if (C == 2) {
         const float4 v = *reinterpret_cast<const float4*>(raw + 4 * n);
         xs0[u] = chan ? v.y : v.x;
@@ -456,7 +481,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
         xs0[u] = v.x;
         xs1[u] = v.y;
       }
-      if (side == 1 && u < 16) {
+      if (side == 1 && u < 8) {
         // SNR partial sums over the first half of the frame (gstpeaq.c:913-918)
         float r0, r1;
         if (C == 2) {
@@ -476,11 +501,11 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     }
   } else {
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int n = lane + 32 * u;
+    for (int u = 0; u < 16; u++) {
+      const int n = t + 64 * u;
       xs0[u] = pcm_at(sig, s0, n_sig, 2 * n, chan, C);
       xs1[u] = pcm_at(sig, s0, n_sig, 2 * n + 1, chan, C);
-      if (side == 1 && u < 16) {
+      if (side == 1 && u < 8) {
         const float r0 = pcm_at(ref_sig, s0, n_ref, 2 * n, chan, C);
         const float r1 = pcm_at(ref_sig, s0, n_ref, 2 * n + 1, chan, C);
         es += (double)(r0 * r0);
@@ -492,74 +517,53 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   }
   __syncthreads();   // staged PCM consumed: the buffers become FFT work space
 
-  // ---- phase 2: window, scatter into FFT order; energy; threshold --------------------
+  // ---- phase 2: window, scatter into FFT order; energy; largest |x| for the threshold ----
   double2* z = reinterpret_cast<double2*>(work);
-  const int slot_lane = fft_slot_rt<10>(lane);
-  bool sure = false, maybe = false;
-  float pa0 = 0.f, pa1 = 0.f;   // |x| of the previous iteration (threshold window)
-  const float thr_f = 200.f / 32768.f;
+  {
+    const int slot_t = fft_slot_rt<10>(t);
+    float amax = 0.f;
 #pragma unroll
-  for (int u = 0; u < 32; u++) {
-    const int n = lane + 32 * u;
-    const float x0 = xs0[u], x1 = xs1[u];
-    const double2 h = *reinterpret_cast<const double2*>(&T->hann[2 * n]);
-    z[slot_lane ^ fft_slot<10>(32 * u)] = make_double2(h.x * x0, h.y * x1);
-    if (u >= 16) {   // samples 1024..2047: float products, double accumulation (fftearmodel.c:508-511)
-      energy += (double)(x0 * x0);
-      energy += (double)(x1 * x1);
-    }
-    if (side == 0) {
-      // 5-sample window sums of |x| in float: decide unless within 1 % of the
-      // threshold (the reference's float recurrence drifts < 2048 * 2^-24)
-      const float a0 = fabsf(x0), a1 = fabsf(x1);
-      const float c1a0 = __shfl_sync(0xffffffffu, a0, (lane - 1) & 31), c1a1 = __shfl_sync(0xffffffffu, a1, (lane - 1) & 31);
-      const float c2a0 = __shfl_sync(0xffffffffu, a0, (lane - 2) & 31), c2a1 = __shfl_sync(0xffffffffu, a1, (lane - 2) & 31);
-      const float q1a0 = __shfl_sync(0xffffffffu, pa0, (lane - 1) & 31), q1a1 = __shfl_sync(0xffffffffu, pa1, (lane - 1) & 31);
-      const float q2a0 = __shfl_sync(0xffffffffu, pa0, (lane - 2) & 31), q2a1 = __shfl_sync(0xffffffffu, pa1, (lane - 2) & 31);
-      const float p1a0 = lane >= 1 ? c1a0 : q1a0, p1a1 = lane >= 1 ? c1a1 : q1a1;
-      const float p2a0 = lane >= 2 ? c2a0 : q2a0, p2a1 = lane >= 2 ? c2a1 : q2a1;
-      const float w_even = a0 + p1a1 + p1a0 + p2a1 + p2a0;   // samples 2n-4 .. 2n
-      const float w_odd = a1 + a0 + p1a1 + p1a0 + p2a1;      // samples 2n-3 .. 2n+1
-      if (n >= 3) {
-        if (w_even >= thr_f * 1.01f) sure = true;
-        else if (w_even >= thr_f * 0.99f) maybe = true;
+    for (int u = 0; u < 16; u++) {
+      const int n = t + 64 * u;
+      const float x0 = xs0[u], x1 = xs1[u];
+      const double2 h = *reinterpret_cast<const double2*>(&T->hann[2 * n]);
+      z[slot_t ^ fft_slot<10>(64 * u)] = make_double2(h.x * x0, h.y * x1);
+      if (u >= 8) {   // samples 1024..2047: float products, double accumulation (fftearmodel.c:508-511)
+        energy += (double)(x0 * x0);
+        energy += (double)(x1 * x1);
       }
-      if (n >= 2) {
-        if (w_odd >= thr_f * 1.01f) sure = true;
-        else if (w_odd >= thr_f * 0.99f) maybe = true;
-      }
-      pa0 = a0;
-      pa1 = a1;
+      // sample 0 never enters a tested window (gstpeaq.c:1088-1096: windows end at i >= 5)
+      if (n > 0) amax = fmaxf(amax, fabsf(x0));
+      amax = fmaxf(amax, fabsf(x1));
     }
-  }
-  energy = warp_sum(energy);
-  if (lane == 0) mail_flags[warp] = energy >= 8000. / (32768. * 32768.);
-  if (side == 0) {
-    bool above = __any_sync(0xffffffffu, sure);
-    if (!above && __any_sync(0xffffffffu, maybe)) above = replay_threshold(sig, s0, n_sig, chan, C, lane);
-    if (lane == 0) mail_flags[2 * C + chan] = above;
-  } else {
-    es = warp_sum(es);
-    en = warp_sum(en);
+    energy = warp_sum(energy);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (side == 1) {
+      es = warp_sum(es);
+      en = warp_sum(en);
+    }
     if (lane == 0) {
-      mail[2 * chan] = es;
-      mail[2 * chan + 1] = en;
+      mail->energy[stream][half] = energy;
+      if (side == 0) mail->maxabs[chan][half] = amax;
+      else {
+        mail->snr_s[chan][half] = es;
+        mail->snr_n[chan][half] = en;
+      }
     }
   }
-  __syncthreads();   // twiddles loaded, flags published (and this warp's scatter complete)
-  if (debug_stop == 1) return;   // development aid: phase timing (PEAQ_B200_K1_STOP)
+  __syncthreads();   // twiddles loaded, mail published, scatter of both halves complete
 
-  // ---- 2048-point real FFT, power spectrum into registers --------------------------
-  warp_fft<10>(z, tw, lane);
-  if (debug_stop == 2) return;
-  double pv[32], p_nyq;
+  // ---- 2048-point real FFT by the stream's 64 threads; power spectrum into registers ----
+  group_fft<10, 64, StreamSync>(z, tw, t, StreamSync{1 + stream});
+  double pv[16], p_nyq = 0.;
   {
     const double lf = T->level_factor_fft;
-    const int sw = fft_swz(lane);
+    const int sw = fft_swz(t);
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int k = lane + 32 * u;
-      const double2 p = z[sw ^ fft_swz(32 * u)];
+    for (int u = 0; u < 16; u++) {
+      const int k = t + 64 * u;
+      const double2 p = z[sw ^ fft_swz(64 * u)];
       const double2 q = z[fft_swz((1024 - k) & 1023)];
       const double er = 0.5 * (p.x + q.x), ei = 0.5 * (p.y - q.y);
       const double orr = 0.5 * (p.y + q.y), oi = -0.5 * (p.x - q.x);
@@ -568,117 +572,137 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
       const double xi = ei + (orr * wi + oi * wr);
       pv[u] = (xr * xr + xi * xi) * lf;   // fftearmodel.c:464-466
     }
-    // bin 1024: X = Re Z[0] - Im Z[0] through the same formula
-    const double2 p = z[fft_swz(0)];
-    const double wr = T->tw2048[1024].x, wi = T->tw2048[1024].y;
-    const double xr = p.x + (p.y * wr - 0. * wi);
-    const double xi = 0. + (p.y * wi + 0. * wr);
-    p_nyq = (xr * xr + xi * xi) * lf;
+    if (t == 0) {
+      // bin 1024: X = Re Z[0] - Im Z[0] through the same formula
+      const double2 p = z[fft_swz(0)];
+      const double wr = T->tw2048[1024].x, wi = T->tw2048[1024].y;
+      const double xr = p.x + (p.y * wr - 0. * wi);
+      const double xi = 0. + (p.y * wi + 0. * wr);
+      p_nyq = (xr * xr + xi * xi) * lf;
+    }
   }
+  (void)p_nyq;   // bin 1024 is outside everything the path reads (see kSpecBins)
 
   double* rec = records + ((size_t)pair * n_chunk_frames + chunk_frame) * L.stride;
 
   // ---- bandwidth on the register-held spectrum (movs.c:783-803) ----------------------
   if (side == 1) {
-    double thr = pv[29];   // bin 928+lane: a start value inside the range 921..1023
-#pragma unroll
-    for (int u = 28; u < 32; u++) {
-      const int k = lane + 32 * u;
-      if (k >= 921 && pv[u] >= thr) thr = pv[u];
-    }
+    double thr = pv[15];   // bin 960 + t: a start value inside the range 921..1023
+    if (896 + t >= 921 && pv[14] >= thr) thr = pv[14];
     thr = warp_max_nonan(thr);
-    if (lane == 0) mail_thr[chan] = thr;
+    if (lane == 0) mail->thr_part[chan][half] = thr;
   }
-  channel_barrier(chan);
-  const double zero_thr = mail_thr[chan];
+  chan_sync(chan);
+  double zero_thr;
+  {
+    const double a = mail->thr_part[chan][0], b = mail->thr_part[chan][1];
+    zero_thr = b > a ? b : a;
+  }
   if (side == 0) {
     int bw_ref = 0;
 #pragma unroll
-    for (int u = 0; u < 29; u++) {
-      const int k = lane + 32 * u;
+    for (int u = 0; u < 15; u++) {
+      const int k = t + 64 * u;
       if (k < 921 && pv[u] > 10. * zero_thr) bw_ref = k + 1;
     }
     bw_ref = warp_max_int(bw_ref);
-    if (lane == 0) mail_flags[3 * C + chan] = bw_ref;
+    if (lane == 0) mail->bw_ref_part[chan][half] = bw_ref;
   }
-  channel_barrier(chan);
+  chan_sync(chan);
+  const int bw_ref = max(mail->bw_ref_part[chan][0], mail->bw_ref_part[chan][1]);
   if (side == 1) {
-    const int bw_ref = mail_flags[3 * C + chan];
     int bw_test = 0;
     if (bw_ref > 346) {
 #pragma unroll
-      for (int u = 0; u < 29; u++) {
-        const int k = lane + 32 * u;
+      for (int u = 0; u < 15; u++) {
+        const int k = t + 64 * u;
         if (k < bw_ref && pv[u] >= 3.16227766016838 * zero_thr) bw_test = k + 1;
       }
       bw_test = warp_max_int(bw_test);
     }
-    if (lane == 0) {
-      int* ints = reinterpret_cast<int*>(rec + L.off_ints);
-      ints[1 + 2 * chan] = bw_ref;
-      ints[2 + 2 * chan] = bw_test;
-    }
+    if (lane == 0) mail->bw_test_part[chan][half] = bw_test;
   }
 
   // ---- weighted power spectrum back into the (now free) FFT buffer ----------------
   double* spec = work;
 #pragma unroll
-  for (int u = 0; u < 32; u++) {
-    const int k = lane + 32 * u;
-    spec[k] = pv[u] * T->earw2[k];   // fftearmodel.c:470-472
+  for (int u = 0; u < 13; u++) {
+    const int k = t + 64 * u;
+    if (k < kSpecBins) spec[k] = pv[u] * T->earw2[k];   // fftearmodel.c:470-472
   }
-  if (lane == 0) spec[1024] = p_nyq * T->earw2[1024];
-  channel_barrier(chan);   // both spectra of the channel visible
-  if (debug_stop == 3) return;
+  chan_sync(chan);   // both spectra of the channel (and bw_test_part) visible
 
-  const double* spec_ref = smem + kTwDoubles + (2 * chan) * kWorkDoubles;
-  const double* spec_test = smem + kTwDoubles + (2 * chan + 1) * kWorkDoubles;
-  double* dlog = smem + kTwDoubles + (2 * chan + 1) * kWorkDoubles + kScratchDlog;
+  double* buf_ref = smem + kTwDoubles + (2 * chan) * kWorkDoubles;
+  double* buf_test = smem + kTwDoubles + (2 * chan + 1) * kWorkDoubles;
+  const double* spec_ref = buf_ref;
+  const double* spec_test = buf_test;
+  double* dlog = buf_test + kScratchDlog;
 
-  // The test warp first does everything that reads BOTH spectra of the channel --
-  // the log spectrum ratio for the EHS (movs.c:1396-1403) and the noise in bands
-  // (movs.c:988-1000) -- and signals it; after that the ref warp may recycle its
-  // buffer for the EHS transforms and never has to wait:
-  //   ref : spreading ......................... -> EHS
-  //   test: ln ratio -> noise in bands -> spreading
-  if (side == 1) {
+  bool ehs_valid = false;
+  for (int w = 0; w < 2 * C; w++)
+    ehs_valid |= mail->energy[w][0] + mail->energy[w][1] >= 8000. / (32768. * 32768.);
+
+  if (role <= 1) {
+    // ---- grouping + internal noise + frequency spreading of one stream ---------------
+    const bool skip = role == 1 && advanced;   // the advanced FFT model only needs the ref excitation
+    double* scratch = role == 0 ? buf_ref + kScratchRef : buf_test + kScratchTest;
+    double* se = scratch + 128;
+    if (!skip) {
+      const double* sp = role == 0 ? spec_ref : spec_test;
+      for (int i = lane; i < B; i += 32) se[i] = group_band(T, sp, i) + T->fft.internal_noise[i];
+    }
+    __threadfence_block();
+    refbuf_arrive(chan);   // this warp no longer reads the ref spectrum
+    if (!skip) {
+      __syncwarp();
+      spread_bands(T, B, scratch, se, scratch + 256, rec + (role * C + chan) * B, lane);
+    }
+    if (role == 0 && lane == 0) {
+      int* ints = reinterpret_cast<int*>(rec + L.off_ints);
+      ints[1 + 2 * chan] = bw_ref;
+      ints[2 + 2 * chan] = max(mail->bw_test_part[chan][0], mail->bw_test_part[chan][1]);
+    }
+  } else {
+    // ---- ln spectrum ratio (movs.c:1396-1403) and noise in bands (movs.c:988-1000), in halves --
+    const int hh = role - 2;
 #pragma unroll 4
-    for (int u = 0; u < 16; u++) {
-      const int i = lane + 32 * u;
+    for (int u = 0; u < 8; u++) {
+      const int i = 256 * hh + lane + 32 * u;
       const double fref = spec_ref[i], ftest = spec_test[i];
       dlog[i] = (fref == 0. && ftest == 0.) ? 0. : log(ftest / fref);
     }
-    for (int i = lane; i < B; i += 32)
+    for (int i = 32 * hh + lane; i < B; i += 64)
       rec[L.off_noise + chan * B + i] = group_band_noise(T, spec_ref, spec_test, i);
     __threadfence_block();
-    channel_arrive(chan);
+    if (role == 3) {
+      refbuf_arrive(chan);
+    } else {
+      refbuf_wait(chan);   // ln ratio complete, ref spectrum dead: its buffer carries the EHS transforms
+      double ehs = 0.;
+      if (ehs_valid) ehs = ehs_channel(T, dlog, buf_ref, tw, lane);
+      if (lane == 0) rec[L.off_ehs + chan] = ehs;
+    }
   }
-  if (debug_stop == 4) return;
 
-  // ---- own stream: grouping + internal noise + frequency spreading -----------
-  if (!(advanced && side == 1)) {
-    double* se = work + kScratchE;
-    for (int i = lane; i < B; i += 32) se[i] = group_band(T, spec, i) + T->fft.internal_noise[i];
-    __syncwarp();
-    spread_bands(T, B, work + kScratchA, se, work + kScratchE2, rec + (side * C + chan) * B, lane);
-  }
-  if (debug_stop == 5) return;
-  if (side == 0) channel_wait(chan);   // ln ratio ready, ref spectrum no longer read by the test warp
-
-  bool ehs_valid = false;
-  for (int w = 0; w < 2 * C; w++) ehs_valid |= mail_flags[w] != 0;
-  if (side == 0) {
-    double ehs = 0.;
-    if (ehs_valid) ehs = ehs_channel(T, dlog, work, tw, lane);
-    if (lane == 0) rec[L.off_ehs + chan] = ehs;
-  }
   if (threadIdx.x == 0) {
+    // is_frame_above_threshold (gstpeaq.c:1081-1099) from the largest |x| per channel: a sample
+    // of 1.01 thr alone carries its window over the threshold, five of less than 0.99 thr / 5
+    // cannot reach it (the float running sum drifts by < 4e-6 while it stays below); only in
+    // between is the recurrence replayed literally
     bool above = false;
     double sum_s = 0., sum_n = 0.;
+    const float thr_f = 200.f / 32768.f;
     for (int c = 0; c < C; c++) {
-      above |= mail_flags[2 * C + c] != 0;
-      sum_s += mail[2 * c];
-      sum_n += mail[2 * c + 1];
+      const float m = fmaxf(mail->maxabs[c][0], mail->maxabs[c][1]);
+      if (m >= thr_f * 1.01f) above = true;
+      sum_s += mail->snr_s[c][0] + mail->snr_s[c][1];
+      sum_n += mail->snr_n[c][0] + mail->snr_n[c][1];
+    }
+    if (!above) {
+      for (int c = 0; c < C && !above; c++) {
+        const float m = fmaxf(mail->maxabs[c][0], mail->maxabs[c][1]);
+        if (5.f * m >= thr_f * 0.99f) above = replay_threshold_serial(ref_sig, s0, n_ref, c, C);
+      }
     }
     rec[L.off_snr] = sum_s;
     rec[L.off_snr + 1] = sum_n;
@@ -690,7 +714,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
 }  // namespace
 
 size_t fft_frames_smem_bytes(int channels) {
-  return sizeof(double) * (kTwDoubles + 2 * channels * kWorkDoubles + 32);
+  return sizeof(double) * (kTwDoubles + 2 * channels * kWorkDoubles) + sizeof(FrameMail);
 }
 
 cudaError_t launch_fft_frames(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
@@ -702,10 +726,9 @@ cudaError_t launch_fft_frames(const DeviceTables* d_tables, PcmView pcm, int n_p
                                        (int)fft_frames_smem_bytes(kMaxChannels));
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)n_chunk_frames * (unsigned)n_pairs);
-  dim3 block(64 * pcm.channels);
-  static const int debug_stop = std::getenv("PEAQ_B200_K1_STOP") ? std::atoi(std::getenv("PEAQ_B200_K1_STOP")) : 0;
+  dim3 block(128 * pcm.channels);
   fft_frames_kernel<<<grid, block, smem, stream>>>(d_tables, pcm, first_frame, n_chunk_frames, records,
-                                                   L, fft_bands, advanced ? 1 : 0, debug_stop);
+                                                   L, fft_bands, advanced ? 1 : 0);
   return cudaGetLastError();
 }
 
