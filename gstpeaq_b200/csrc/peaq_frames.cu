@@ -136,9 +136,19 @@ __device__ __forceinline__ double noise_bin(const double* spec_ref, const double
 __device__ __forceinline__ double group_band_noise(const DeviceTables* __restrict__ T,
                                                    const double* spec_ref, const double* spec_test,
                                                    int i) {
+  // wl N[lo] + wu N[hi] + N[lo+1] + ... + N[hi-1] in the reference's order, through one copy of
+  // the (long) square-root code: the inner bins carry weight 1, which multiplies exactly
   const int lo = T->band_lo[i], hi = T->band_hi[i];
-  double p = T->band_wl[i] * noise_bin(spec_ref, spec_test, lo) + T->band_wu[i] * noise_bin(spec_ref, spec_test, hi);
-  for (int k = lo + 1; k < hi; k++) p += noise_bin(spec_ref, spec_test, k);
+  const double wl = T->band_wl[i], wu = T->band_wu[i];
+  double p = 0.;
+  const int n_terms = hi > lo ? hi - lo + 1 : 2;   // both edge terms exist even when lo == hi
+#pragma unroll 1
+  for (int j = 0; j < n_terms; j++) {
+    const int k = j == 0 ? lo : (j == 1 ? hi : lo + j - 1);
+    const double w = j == 0 ? wl : (j == 1 ? wu : 1.);
+    const double v = w * noise_bin(spec_ref, spec_test, k);
+    p = j == 0 ? v : p + v;
+  }
   return p < 1e-12 ? 1e-12 : p;
 }
 
@@ -148,8 +158,8 @@ __device__ __forceinline__ double group_band_noise(const DeviceTables* __restric
 __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* sa, double* se,
                              double* se2, double* __restrict__ out, int lane) {
   const double dz02 = 0.2 * T->dz;
-  // four bands per lane, interleaved for instruction-level parallelism
-#pragma unroll
+  // four bands per lane, two at a time (instruction-level parallelism against code size)
+#pragma unroll 2
   for (int m = 0; m < 4; m++) {
     const int i = lane + 32 * m;
     const int ii = i < B ? i : B - 1;
@@ -326,7 +336,7 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
   double csum = 0.;
 #pragma unroll
   for (int e = 0; e < 8; e++) {
-    c[e] = c[e] / sqrt(d0 * dk);
+    c[e] = c[e] * rsqrt(d0 * dk);   // c / sqrt(d0 dk) (movs.c:1415); same zero / NaN classes
     csum += c[e];
     dk += term[e];
   }
@@ -446,7 +456,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   const float* __restrict__ sig = side ? test_sig : ref_sig;
   // whole frame inside both signals and 16-byte aligned: stage it with two TMA bulk
   // copies (ref -> stream 0's buffer, test -> stream 1's buffer, both still unused);
-  // otherwise (last, zero-padded frame; odd strides) fall back to guarded scalar loads
+  // otherwise (last, zero-padded frame; odd strides) a guarded copy fills the same buffers
   const bool tma_ok = (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(test_sig) & 15) == 0 &&
                       s0 + kFftFrame <= n_ref && s0 + kFftFrame <= n_test;
@@ -463,11 +473,21 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     }
   }
 
+  else {
+    // guarded copy of the frame (zeros past the end of either signal) into the same buffers
+    const unsigned long long base = s0 * (unsigned long long)C;
+    for (int i = threadIdx.x; i < kFftFrame * C; i += blockDim.x) {
+      raw_ref[i] = base + i < n_ref * C ? __ldg(ref_sig + base + i) : 0.f;
+      raw_test[i] = base + i < n_test * C ? __ldg(test_sig + base + i) : 0.f;
+    }
+    __syncthreads();
+  }
+
   // ---- phase 1: this thread's 32 samples (complex points n = t + 64 u) into registers ----
   float xs0[16], xs1[16];
   double energy = 0., es = 0., en = 0.;
-  if (tma_ok) {
-    mbar_wait(&mail->mbar, 0);
+  if (tma_ok) mbar_wait(&mail->mbar, 0);
+  {
     const float* raw = side ? raw_test : raw_ref;
 #pragma unroll
     for (int u = 0; u < 16; u++) {
@@ -493,21 +513,6 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
           r0 = v.x;
           r1 = v.y;
         }
-        es += (double)(r0 * r0);
-        es += (double)(r1 * r1);
-        en += (double)((r0 - xs0[u]) * (r0 - xs0[u]));
-        en += (double)((r1 - xs1[u]) * (r1 - xs1[u]));
-      }
-    }
-  } else {
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int n = t + 64 * u;
-      xs0[u] = pcm_at(sig, s0, n_sig, 2 * n, chan, C);
-      xs1[u] = pcm_at(sig, s0, n_sig, 2 * n + 1, chan, C);
-      if (side == 1 && u < 8) {
-        const float r0 = pcm_at(ref_sig, s0, n_ref, 2 * n, chan, C);
-        const float r1 = pcm_at(ref_sig, s0, n_ref, 2 * n + 1, chan, C);
         es += (double)(r0 * r0);
         es += (double)(r1 * r1);
         en += (double)((r0 - xs0[u]) * (r0 - xs0[u]));
@@ -665,7 +670,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   } else {
     // ---- ln spectrum ratio (movs.c:1396-1403) and noise in bands (movs.c:988-1000), in halves --
     const int hh = role - 2;
-#pragma unroll 4
+#pragma unroll 2
     for (int u = 0; u < 8; u++) {
       const int i = 256 * hh + lane + 32 * u;
       const double fref = spec_ref[i], ftest = spec_test[i];
