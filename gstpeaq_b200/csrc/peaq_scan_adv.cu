@@ -36,6 +36,7 @@ constexpr double kSlopeA = 0.993355506255034;   // fbearmodel.c:49
 constexpr double kDist = 0.921851456499719;     // fbearmodel.c:50
 constexpr double kCl = 0.0802581846102741;      // fbearmodel.c:51
 constexpr double kLnDist = -0.08137117849224008;  // ln(kDist)
+constexpr double kKappa = 0.07067810761028887;    // -0.2 * 10 / ln(10) * ln(kDist)
 enum { kStInit = 0, kStNormal = 1, kStTentative = 2 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -67,6 +68,9 @@ struct FbSmem {
   double md[kMaxChannels][2][3][kFbBands];    // [ref|test][prev, filt_loud, filt_deriv]
   double pa[kMaxChannels][2][kFbBands];
   double acc[kMaxChannels][3][kAccFields];
+  double mod[2 * kMaxChannels][kFbBands];     // modulation of every stream (written by its own warp)
+  double ad[kMaxChannels][2][kFbBands];       // spectrally adapted patterns, ref | test (written by the ref warp)
+  double tsum[kMaxChannels][2];               // band sums computed by the test warp: missing components, lin. dist.
   int latch;
 };
 
@@ -77,7 +81,7 @@ struct SpreadSmem {
   double re[kFbBands][kSpPad];
   double im[kFbBands][kSpPad];
   double cu[kFbBands][kSpPad];   // DIST^s, then the smoothed slope
-  double slope0[kFbBands];       // 24 + 230 / fc
+  double slope0[kFbBands];       // (24 + 230 / fc) ln DIST
 };
 
 __global__ void __launch_bounds__(2 * kSpTile, 6)
@@ -95,7 +99,7 @@ fb_spread_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__
   double cu_state = 0.;
   if (tid < kFbBands) {
     cu_state = st_stream[tid];
-    sm.slope0[tid] = 24 + 230 / T->fb.fc[tid];
+    sm.slope0[tid] = (24 + 230 / T->fb.fc[tid]) * kLnDist;   // ln DIST^(24 + 230 / fc)
   }
   const double2* __restrict__ my_out = fbout + (size_t)stream * kFbBands * n_sub;
   double* __restrict__ my_e = energy + (size_t)stream * kFbBands * n_sub;
@@ -105,16 +109,18 @@ fb_spread_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__
     const int nt = (int)min((unsigned)kSpTile, valid - s0);
     // ---- level dependent slope of every (band, sub-step) (fbearmodel.c:326-331) ----
     if (t < nt) {
-#pragma unroll 4
+      // DIST^max(4, s0 - 0.2 L) with L = 10 log10 p, written as exp(min(4 ln DIST, c0 + kappa ln p)):
+      // one ln and one exp per value instead of log10 + exp (same value to ~1e-16)
+      double2 o[kFbBands / 2];
+#pragma unroll
+      for (int k = 0; k < kFbBands / 2; k++) o[k] = my_out[(size_t)(part + 2 * k) * n_sub + s0 + t];
+#pragma unroll
       for (int k = 0; k < kFbBands / 2; k++) {
         const int b = part + 2 * k;
-        const double2 o = my_out[(size_t)b * n_sub + s0 + t];
-        const double L = 10 * log10(o.x * o.x + o.y * o.y);
-        const double slope = sm.slope0[b] - 0.2 * L;
-        const double sl_eff = 4 > slope ? 4 : slope;      // MAX (4, ...)
-        sm.re[b][t] = o.x;
-        sm.im[b][t] = o.y;
-        sm.cu[b][t] = exp(sl_eff * kLnDist);               // DIST^s
+        const double e = sm.slope0[b] + kKappa * log(o[k].x * o[k].x + o[k].y * o[k].y);
+        sm.re[b][t] = o[k].x;
+        sm.im[b][t] = o[k].y;
+        sm.cu[b][t] = exp(e < 4 * kLnDist ? e : 4 * kLnDist);
       }
     }
     __syncthreads();
@@ -251,6 +257,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
     if (threadIdx.x == 0) sm.latch = 0;   // set after the first barrier, read after the second
     double nxt[2][6];
     if (f + 1 < end) load_frame(fl + 1, nxt);
+    double mod_own[2] = {0., 0.}, avl_own[2] = {0., 0.};
     // ---- backward masking, noise, forward masking (fbearmodel.c:371-395) -------
     // E0_buf[i] (i = 0 newest) is cur[5 - i] for i <= 5 and prev[10 - i] beyond
 #pragma unroll
@@ -266,6 +273,21 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
         exc[sl] = a_ear * exc[sl] + (1. - a_ear) * U;
         sm.ex_u[warp][b] = U;
         sm.ex_e[warp][b] = exc[sl];
+        {
+          // modulation of this stream (modpatt.c:234-250): needs nothing but its own unsmeared
+          // excitation, so every warp does its own
+          const double a_proc = sm.cst[kCAProc][b];
+          const double loud = exp(0.3 * log(U));
+          const double fd = a_proc * sm.md[chan][side][2][b] +
+                            (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][side][0][b]));
+          const double fl_ = a_proc * sm.md[chan][side][1][b] + (1. - a_proc) * loud;
+          sm.md[chan][side][2][b] = fd;
+          sm.md[chan][side][1][b] = fl_;
+          sm.md[chan][side][0][b] = loud;
+          mod_own[sl] = fd / (1. + fl_ / 0.3);
+          avl_own[sl] = fl_;
+          sm.mod[warp][b] = mod_own[sl];
+        }
         if (dbg) {
           // [pair][frame][stream][U|E][40]
           double* d = dbg + (((size_t)pair * n_chunk_frames + fl) * 2 * C + warp) * 2 * kFbBands;
@@ -282,7 +304,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
 
     // ---- channel processing on the ref warp (apply_ear_model_and_preprocess) ----
     // per-band values the MOV section needs, kept in registers across the barrier
-    double adr[2], adt[2], mod_r[2], mod_t[2], avl_r[2];
+    double adr[2], adt[2];
     if (side == 0) {
       double lcr[2], lct[2];
       double p_num = 0., p_den = 0., l_r = 0., l_t = 0.;
@@ -347,7 +369,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
-        adr[sl] = adt[sl] = mod_r[sl] = mod_t[sl] = avl_r[sl] = 0.;
+        adr[sl] = adt[sl] = 0.;
         if (b < kFbBands) {
           const double a_proc = sm.cst[kCAProc][b];
           // leveladapter.c:315-339 with band_count 40: m1 = min(k,1), m2 = min(40-k-1,1)
@@ -365,28 +387,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           sm.lv[chan][5][b] = pct;
           adr[sl] = lcr[sl] * pcr;
           adt[sl] = lct[sl] * pct;
-          // modulation (modpatt.c:234-250), ref then test
-          {
-            const double loud = exp(0.3 * log(sm.ex_u[2 * chan][b]));
-            const double fd = a_proc * sm.md[chan][0][2][b] +
-                              (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][0][0][b]));
-            const double fl_ = a_proc * sm.md[chan][0][1][b] + (1. - a_proc) * loud;
-            sm.md[chan][0][2][b] = fd;
-            sm.md[chan][0][1][b] = fl_;
-            sm.md[chan][0][0][b] = loud;
-            mod_r[sl] = fd / (1. + fl_ / 0.3);
-            avl_r[sl] = fl_;
-          }
-          {
-            const double loud = exp(0.3 * log(sm.ex_u[2 * chan + 1][b]));
-            const double fd = a_proc * sm.md[chan][1][2][b] +
-                              (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][1][0][b]));
-            const double fl_ = a_proc * sm.md[chan][1][1][b] + (1. - a_proc) * loud;
-            sm.md[chan][1][2][b] = fd;
-            sm.md[chan][1][1][b] = fl_;
-            sm.md[chan][1][0][b] = loud;
-            mod_t[sl] = fd / (1. + fl_ / 0.3);
-          }
+          sm.ad[chan][0][b] = adr[sl];
+          sm.ad[chan][1][b] = adt[sl];
         }
       }
     }
@@ -394,88 +396,107 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
     if (loud_frame == UINT_MAX && sm.latch) loud_frame = frame_counter;
 
     // ---- MOVs of the filter-bank clock (gstpeaq.c:987-1007) --------------------
+    // band sums: the ref warp takes the modulation difference and the noise loudness, the test
+    // warp the two other loudness terms; lane 0 of the ref warp then feeds the accumulators
+    const bool md_gate = frame_counter >= 125;
+    const bool nl_gate = md_gate && frame_counter - 13 >= loud_frame;
+    double s_md = 0., s_wt = 0., s_nl = 0.;
     if (side == 0) {
-      const bool md_gate = frame_counter >= 125;
-      const bool nl_gate = md_gate && frame_counter - 13 >= loud_frame;
-      double s_md = 0., s_wt = 0., s_nl = 0., s_mc = 0., s_ld = 0.;
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
         if (b < kFbBands) {
-          const double in_noise = sm.cst[kCNoise][b];
+          const double mod_r = mod_own[sl], mod_t = sm.mod[warp + 1][b];
           if (md_gate) {   // movs.c:226-242 with levWt = 1 (no second accumulator)
-            const double diff = fabs(mod_r[sl] - mod_t[sl]);
-            s_md += diff / (1. + mod_r[sl]);
-            s_wt += avl_r[sl] / (avl_r[sl] + 1. * sm.cst[kCNoise03][b]);
+            const double diff = fabs(mod_r - mod_t);
+            s_md += diff / (1. + mod_r);
+            s_wt += avl_own[sl] / (avl_own[sl] + 1. * sm.cst[kCNoise03][b]);
           }
-          if (nl_gate) {
-            // peaq_mov_noise_loud_asym (movs.c:551-577): the missing-components
-            // term swaps ref/test patterns AND modulation (settings.h:47)
-            s_nl += nl_term(2.5, 0.3, 1., in_noise, mod_r[sl], mod_t[sl], adr[sl], adt[sl]);
-            s_mc += nl_term(1.5, 0.15, 1., in_noise, mod_t[sl], mod_r[sl], adt[sl], adr[sl]);
-            // peaq_mov_lin_dist (movs.c:679-706): ref modulation on both sides,
-            // adapted ref pattern vs ref excitation
-            s_ld += nl_term(1.5, 0.15, 1., in_noise, mod_r[sl], mod_r[sl], adr[sl], sm.ex_e[2 * chan][b]);
-          }
+          if (nl_gate)   // peaq_mov_noise_loud_asym, first term (movs.c:551-577)
+            s_nl += nl_term(2.5, 0.3, 1., sm.cst[kCNoise][b], mod_r, mod_t, adr[sl], adt[sl]);
         }
       }
       s_md = warp_sum(s_md);
       s_wt = warp_sum(s_wt);
       s_nl = warp_sum(s_nl);
-      s_mc = warp_sum(s_mc);
-      s_ld = warp_sum(s_ld);
+    } else {
+      double s_mc = 0., s_ld = 0.;
+      if (nl_gate) {
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+          const int b = lane + 32 * sl;
+          if (b < kFbBands) {
+            const double in_noise = sm.cst[kCNoise][b];
+            const double mod_t = mod_own[sl], mod_r = sm.mod[warp - 1][b];
+            const double a_r = sm.ad[chan][0][b], a_t = sm.ad[chan][1][b];
+            // the missing-components term swaps ref/test patterns AND modulation (settings.h:47)
+            s_mc += nl_term(1.5, 0.15, 1., in_noise, mod_t, mod_r, a_t, a_r);
+            // peaq_mov_lin_dist (movs.c:679-706): ref modulation on both sides,
+            // adapted ref pattern vs ref excitation
+            s_ld += nl_term(1.5, 0.15, 1., in_noise, mod_r, mod_r, a_r, sm.ex_e[2 * chan][b]);
+          }
+        }
+        s_mc = warp_sum(s_mc);
+        s_ld = warp_sum(s_ld);
+      }
       if (lane == 0) {
-        double (*a)[kAccFields] = sm.acc[chan];
-        // peaq_movaccum_set_tentative on the three fb-clock accumulators (gstpeaq.c:974-979)
-        int st_new = status;
-        if (!above) {
-          if (status == kStNormal) {
-            for (int k = 0; k < 3; k++) {
-              a[k][5] = a[k][0];
-              a[k][6] = a[k][1];
-              a[k][7] = a[k][2];
-            }
-            st_new = kStTentative;
+        sm.tsum[chan][0] = s_mc;
+        sm.tsum[chan][1] = s_ld;
+      }
+    }
+    __syncthreads();   // the test warp's sums visible
+    if (side == 0 && lane == 0) {
+      const double s_mc = sm.tsum[chan][0], s_ld = sm.tsum[chan][1];
+      double (*a)[kAccFields] = sm.acc[chan];
+      // peaq_movaccum_set_tentative on the three fb-clock accumulators (gstpeaq.c:974-979)
+      int st_new = status;
+      if (!above) {
+        if (status == kStNormal) {
+          for (int k = 0; k < 3; k++) {
+            a[k][5] = a[k][0];
+            a[k][6] = a[k][1];
+            a[k][7] = a[k][2];
           }
-        } else {
-          st_new = kStNormal;
+          st_new = kStTentative;
         }
-        if (st_new != kStInit) {
-          if (md_gate) {
-            // MODE_RMS: weight squared (movaccum.c:375-379); value scaled by 100/sqrt(B) (movs.c:243-244)
-            const double val = s_md * (100. / sqrt((double)kFbBands));
-            double w = s_wt;
-            w *= w;
-            a[0][0] += w * val * val;
-            a[0][1] += w;
-          }
-          if (nl_gate) {
-            double nl = s_nl * (24. / kFbBands);
-            if (nl < 0.1) nl = 0.;                       // NLmin (movs.c:740-741)
-            double mc = s_mc * (24. / kFbBands);
-            if (mc < 0.) mc = 0.;
-            double ld = s_ld * (24. / kFbBands);
-            if (ld < 0.) ld = 0.;
-            // MODE_RMS_ASYM (movaccum.c:380-385): field 2 holds the second numerator
-            a[1][0] += nl * nl;
-            a[1][2] += mc * mc;
-            a[1][1] += 1.;
-            a[2][0] += 1. * ld;                          // MODE_AVG, weight 1
-            a[2][1] += 1.;
-          }
+      } else {
+        st_new = kStNormal;
+      }
+      if (st_new != kStInit) {
+        if (md_gate) {
+          // MODE_RMS: weight squared (movaccum.c:375-379); value scaled by 100/sqrt(B) (movs.c:243-244)
+          const double val = s_md * (100. / sqrt((double)kFbBands));
+          double w = s_wt;
+          w *= w;
+          a[0][0] += w * val * val;
+          a[0][1] += w;
         }
-        if (dbg) {
-          double* d = dbg + (size_t)gridDim.x * n_chunk_frames * 2 * C * 2 * kFbBands +
-                      (((size_t)pair * n_chunk_frames + fl) * C + chan) * 8;
+        if (nl_gate) {
           double nl = s_nl * (24. / kFbBands);
-          if (nl < 0.1) nl = 0.;
-          d[0] = md_gate ? s_md * (100. / sqrt((double)kFbBands)) : 0.;
-          d[1] = md_gate ? s_wt : 0.;
-          d[2] = nl_gate ? nl : 0.;
-          d[3] = nl_gate ? s_mc * (24. / kFbBands) : 0.;
-          d[4] = nl_gate ? s_ld * (24. / kFbBands) : 0.;
-          d[5] = above;
+          if (nl < 0.1) nl = 0.;                       // NLmin (movs.c:740-741)
+          double mc = s_mc * (24. / kFbBands);
+          if (mc < 0.) mc = 0.;
+          double ld = s_ld * (24. / kFbBands);
+          if (ld < 0.) ld = 0.;
+          // MODE_RMS_ASYM (movaccum.c:380-385): field 2 holds the second numerator
+          a[1][0] += nl * nl;
+          a[1][2] += mc * mc;
+          a[1][1] += 1.;
+          a[2][0] += 1. * ld;                          // MODE_AVG, weight 1
+          a[2][1] += 1.;
         }
+      }
+      if (dbg) {
+        double* d = dbg + (size_t)gridDim.x * n_chunk_frames * 2 * C * 2 * kFbBands +
+                    (((size_t)pair * n_chunk_frames + fl) * C + chan) * 8;
+        double nl = s_nl * (24. / kFbBands);
+        if (nl < 0.1) nl = 0.;
+        d[0] = md_gate ? s_md * (100. / sqrt((double)kFbBands)) : 0.;
+        d[1] = md_gate ? s_wt : 0.;
+        d[2] = nl_gate ? nl : 0.;
+        d[3] = nl_gate ? s_mc * (24. / kFbBands) : 0.;
+        d[4] = nl_gate ? s_ld * (24. / kFbBands) : 0.;
+        d[5] = above;
       }
     }
     if (!above) {
@@ -484,8 +505,10 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
       status = kStNormal;
     }
     frame_counter++;
-    __syncthreads();
+    // no barrier here: everything the next frame overwrites before its first barrier was last
+    // read before the one above
   }
+  __syncthreads();
 
   // ---- store state, publish the channel-averaged MOVs ----------------------------
 #pragma unroll
