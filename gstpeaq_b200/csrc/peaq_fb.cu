@@ -96,41 +96,31 @@ struct Biquads {
 
 constexpr int kHpBlock = 16;   // samples per register block (input prefetch / 128-byte output rows)
 
-// One thread per (pair, side) runs the C channel filters of that signal in
-// lock step (independent chains => instruction-level parallelism); input is
-// fetched 16 samples ahead with 128-bit loads, output written as full 128-byte
-// rows.  The recurrence itself is inherently sequential in time.
+// One thread per stream (pair, channel, side).  The recurrence is inherently sequential
+// in time and its loop-carried chain (multiply, add, add per section) is what bounds the
+// kernel, so a thread carries ONE filter: with both channels of a signal in one thread the
+// half-rate FP64 pipe of the (single) resident warp became the limit instead.  Input is
+// fetched 16 samples ahead with 128-bit loads (the two channel threads of a signal read the
+// same interleaved lines; the second read hits L1), output written as 128-byte rows.
 template <int C>
-__global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_sigs,
+__global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams,
                              unsigned long long t0, unsigned chunk_samples,
                              double* __restrict__ hp, size_t hp_stride,
                              double* __restrict__ hp_state /* [stream][kHpStateDoubles] */, int first_chunk) {
-  const int sig_idx = blockIdx.x * blockDim.x + threadIdx.x;   // pair * 2 + side
-  if (sig_idx >= n_sigs) return;
-  const int pair = sig_idx >> 1, side = sig_idx & 1;
+  const int stream = blockIdx.x * blockDim.x + threadIdx.x;   // pair * 2C + 2c + side, as everywhere
+  if (stream >= n_streams) return;
+  const int pair = stream / (2 * C), c = (stream >> 1) % C, side = stream & 1;
   const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
   const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
   const bool aligned = (reinterpret_cast<uintptr_t>(sig) & 15) == 0;
-  Biquads f[C];
-  double* out[C];
-#pragma unroll
-  for (int c = 0; c < C; c++) {
-    const int stream = pair * 2 * C + 2 * c + side;   // stream order of the other kernels
-    out[c] = hp + (size_t)stream * hp_stride;
-    double* st = hp_state + (size_t)stream * kHpStateDoubles;
-    if (first_chunk) {
-      f[c] = Biquads{0, 0, 0, 0, 0, 0};
-    } else {
-      f[c] = Biquads{st[0], st[1], st[2], st[3], st[4], st[5]};
-    }
+  double* out = hp + (size_t)stream * hp_stride;
+  double* st = hp_state + (size_t)stream * kHpStateDoubles;
+  Biquads f = first_chunk ? Biquads{0, 0, 0, 0, 0, 0} : Biquads{st[0], st[1], st[2], st[3], st[4], st[5]};
+  {
     // history for the FIR bank: last kFbHist samples of the previous chunk
-    double2* o2 = reinterpret_cast<double2*>(out[c]);
-    if (first_chunk) {
-      for (int i = 0; i < kFbHist / 2; i++) o2[i] = make_double2(0., 0.);
-    } else {
-      const double2* src = reinterpret_cast<const double2*>(st + 6);   // saved by the previous chunk
-      for (int i = 0; i < kFbHist / 2; i++) o2[i] = src[i];
-    }
+    double2* o2 = reinterpret_cast<double2*>(out);
+    const double2* src = reinterpret_cast<const double2*>(st + 6);   // saved by the previous chunk
+    for (int i = 0; i < kFbHist / 2; i++) o2[i] = first_chunk ? make_double2(0., 0.) : src[i];
   }
   const double lf = T->level_factor_fb;
   // samples past the end of the item are zero (do_flush pads the last frame,
@@ -160,36 +150,32 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   };
   if (chunk_samples) fetch(0);
   for (unsigned i0 = 0; i0 < chunk_samples; i0 += kHpBlock) {
-    float x[C][kHpBlock];
+    float x[kHpBlock];
 #pragma unroll
     for (int q = 0; q < kVec; q++) {
       const float e[4] = {nxt[q].x, nxt[q].y, nxt[q].z, nxt[q].w};
+      if (C == 1) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) x[(4 * q + r) % C][(4 * q + r) / C] = e[r];
+        for (int r = 0; r < 4; r++) x[4 * q + r] = e[r];
+      } else {   // interleaved stereo: samples 2q, 2q+1 of channel c
+        x[2 * q] = c ? e[1] : e[0];
+        x[2 * q + 1] = c ? e[3] : e[2];
+      }
     }
     if (i0 + kHpBlock < chunk_samples) fetch(i0 + kHpBlock);
-    double y[C][kHpBlock];
+    double y[kHpBlock];
 #pragma unroll
-    for (int k = 0; k < kHpBlock; k++)
+    for (int k = 0; k < kHpBlock; k++) y[k] = f.step(x[k] * lf);   // fbearmodel.c:289
+    double2* o = reinterpret_cast<double2*>(out + kFbHist + i0);
 #pragma unroll
-      for (int c = 0; c < C; c++) y[c][k] = f[c].step(x[c][k] * lf);   // fbearmodel.c:289
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      double2* o = reinterpret_cast<double2*>(out[c] + kFbHist + i0);
-#pragma unroll
-      for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[c][2 * k], y[c][2 * k + 1]);
-    }
+    for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[2 * k], y[2 * k + 1]);
   }
-#pragma unroll
-  for (int c = 0; c < C; c++) {
-    double* st = hp_state + (size_t)(pair * 2 * C + 2 * c + side) * kHpStateDoubles;
-    st[0] = f[c].x1; st[1] = f[c].x2; st[2] = f[c].y1a; st[3] = f[c].y2a; st[4] = f[c].y1b; st[5] = f[c].y2b;
-    // the last kFbHist filtered samples ([history | chunk] is contiguous in `out`) become
-    // the next chunk's history; works for chunks shorter than the history too
-    double2* dst = reinterpret_cast<double2*>(st + 6);
-    const double2* src = reinterpret_cast<const double2*>(out[c] + chunk_samples);
-    for (int i = 0; i < kFbHist / 2; i++) dst[i] = src[i];
-  }
+  st[0] = f.x1; st[1] = f.x2; st[2] = f.y1a; st[3] = f.y2a; st[4] = f.y1b; st[5] = f.y2b;
+  // the last kFbHist filtered samples ([history | chunk] is contiguous in `out`) become
+  // the next chunk's history; works for chunks shorter than the history too
+  double2* dst = reinterpret_cast<double2*>(st + 6);
+  const double2* src = reinterpret_cast<const double2*>(out + chunk_samples);
+  for (int i = 0; i < kFbHist / 2; i++) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -534,16 +520,16 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
                          unsigned long long t0, unsigned chunk_samples,
                          double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
                          cudaStream_t stream) {
-  const int n_sigs = n_pairs * 2;
-  if (n_sigs <= 0) return cudaSuccess;
-  // few threads per block so the signals spread over all SMs (latency-bound scan)
+  const int n_streams = n_pairs * 2 * pcm.channels;
+  if (n_streams <= 0) return cudaSuccess;
+  // few threads per block so the streams spread over all SMs (latency-bound scan)
   const int block = 32;
-  const int grid = (n_sigs + block - 1) / block;
+  const int grid = (n_streams + block - 1) / block;
   if (pcm.channels == 2) {
-    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, hp, hp_stride, hp_state,
+    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_streams, t0, chunk_samples, hp, hp_stride, hp_state,
                                                 first_chunk ? 1 : 0);
   } else {
-    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_sigs, t0, chunk_samples, hp, hp_stride, hp_state,
+    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_streams, t0, chunk_samples, hp, hp_stride, hp_state,
                                                 first_chunk ? 1 : 0);
   }
   return cudaGetLastError();
