@@ -204,11 +204,11 @@ def measured_peak_gbs():
 
 
 def ncu_traffic_per_frame():
-    """dram bytes per PEAQ frame of the frame kernel from the committed ncu capture, or None"""
+    """dram bytes per PEAQ frame of the mode's dominant kernel from the committed ncu capture, or None"""
     p = os.path.join(ROOT, "profiles", "ncu_frame_kernel.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["dram_bytes_per_frame"])
+            return float(json.load(open(p))["dram_bytes_per_frame" if MODE == "basic" else "bank_dram_bytes_per_frame"])
         except Exception:
             return None
     return None
@@ -259,12 +259,13 @@ def our_arm(args):
     launches0 = eng.launch_count()
     barrier()
     t0 = time.perf_counter()
-    dev_ms = k1_ms = k2_ms = 0.0
+    dev_ms = k1_ms = k2_ms = bank_ms = 0.0
     for _ in range(args.steps):
         out = step()
         dev_ms += eng.last_ms(0)       # CUDA events on the engine's stream
         k1_ms += eng.last_ms(1)
         k2_ms += eng.last_ms(2)
+        bank_ms += eng.last_ms(5)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = eng.launch_count() - launches0
@@ -274,9 +275,9 @@ def our_arm(args):
     # timed steps: it moves 128 B per pair once per job
     if dist is not None:
         full = parallel.gather_results(out, n_global, torch.device("cuda", local_rank))
-        t = torch.tensor([dev_ms, wall_ms, k1_ms, k2_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, wall_ms, k1_ms, k2_ms, bank_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, k1_ms, k2_ms = [float(x) for x in t.tolist()]
+        dev_ms, wall_ms, k1_ms, k2_ms, bank_ms = [float(x) for x in t.tolist()]
     else:
         full = out
     frames_step = int(full["frames_fft"].sum())
@@ -333,19 +334,23 @@ def our_arm(args):
         return 0
 
     peak, peak_src = measured_peak_gbs()
-    # dominant kernel: fft_frames.  algorithmic bytes per launch = 16384 B x frames in the launch;
-    # duration = CUDA-event time of the launches (per GPU: frames of one rank)
+    # dominant kernel: fft_frames_kernel (basic) / fb_bank_rec_kernel (advanced).  Algorithmic
+    # bytes per launch = 16384 B x the frames the launch covers (both modes read the
+    # PCM once per ear model); duration = CUDA-event time of those launches inside the timed
+    # steps (per GPU: the frames of one rank)
     frames_rank = count * fpp
-    k1_s = ((k1_ms if MODE == "basic" else dev_ms) / args.steps) / 1e3
-    achieved = frames_rank * BYTES_PER_FRAME / k1_s / 1e9
+    dom_ms = (k1_ms if MODE == "basic" else bank_ms) / args.steps
+    achieved = frames_rank * BYTES_PER_FRAME / (dom_ms / 1e3) / 1e9
     traffic = ncu_traffic_per_frame()
-    roofline = {"bound": "hbm", "kernel": "fft_frames_kernel" if MODE == "basic" else "fb_bank_kernel + fb_scan_kernel (FP64 bound; HBM figure uses the whole step)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "fft_frames_kernel" if MODE == "basic" else "fb_bank_rec_kernel",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": traffic * frames_rank if traffic else None,
                 "algorithmic_bytes_per_launch_set": frames_rank * BYTES_PER_FRAME,
-                "kernel_ms_per_step": k1_ms / args.steps, "scan_kernel_ms_per_step": k2_ms / args.steps,
-                "kernel_share_of_step": k1_ms / dev_ms,
-                "note": "FP64 ALU/transcendental bound in practice (SURVEY 8d); HBM fraction reported as the north star asks"}
+                "kernel_ms_per_step": dom_ms, "frame_kernel_ms_per_step": k1_ms / args.steps,
+                "scan_kernel_ms_per_step": k2_ms / args.steps,
+                "kernel_share_of_step": dom_ms * args.steps / dev_ms,
+                "note": "FP64 latency/issue bound in practice (DESIGN.md 3); HBM fraction reported as the north star asks"}
 
     # ---- CPU baseline (N = 1 only): bounded sample on the host cores ------------
     cpu = None

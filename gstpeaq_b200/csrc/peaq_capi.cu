@@ -163,7 +163,7 @@ struct Engine {
   std::vector<std::vector<unsigned>> plan_hold_nf;
   std::vector<EventPair> events;
   size_t events_used = 0;
-  double ms[5] = {0, 0, 0, 0, 0};
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // see peaq_b200_engine_last_ms; [7]: flags + DC-reject scan
   uint64_t launches = 0;
   bool keep_records = false;
   RecordLayout last_layout = {};
@@ -447,15 +447,18 @@ struct Engine {
       while (first < max_fb_frames) {
         const unsigned n = (unsigned)std::min<size_t>(chunk, max_fb_frames - first);
         const unsigned n_sub = n * 6, samples = n * kFbFrame;
-        if ((rc = timer_begin(4))) return rc;
+        if ((rc = timer_begin(7))) return rc;
         PEAQ_CUDA(launch_fb_flags(pcm_fb, n_pairs, first, n, d_fbflags, stream));
         PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
                                hp_stride, d_hp_state, first == 0 && reset_state, stream));
+        if ((rc = timer_end())) return rc;
         // PEAQ_B200_FB_DIRECT=1: all 40 filters as direct FIRs (development aid / cross-check)
         static const bool fb_direct = std::getenv("PEAQ_B200_FB_DIRECT") && std::atoi(std::getenv("PEAQ_B200_FB_DIRECT"));
+        if ((rc = timer_begin(5))) return rc;
         PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, d_hp_state,
                                  first == 0 && reset_state, fb_direct, stream));
-        if (!fb_direct) launches++;
+        if ((rc = timer_end())) return rc;
+        if ((rc = timer_begin(6))) return rc;
         PEAQ_CUDA(launch_fb_spread(d_tables, d_fbout, n_sub, pcm_fb.n_frames, first, d_state, A, d_fbenergy,
                                    n_pairs, stream));
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,
@@ -521,7 +524,7 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     if (n_pairs > 1 && ns[p] * C > b->pair_stride)
       return fail(PEAQ_B200_ERR_INVALID, "pair_stride smaller than an item");
   }
-  for (int i = 0; i < 5; i++) e->ms[i] = 0;
+  for (int i = 0; i < 8; i++) e->ms[i] = 0;
   cudaEvent_t t0, t1;
   PEAQ_CUDA(cudaEventCreate(&t0));
   PEAQ_CUDA(cudaEventCreate(&t1));
@@ -843,7 +846,8 @@ int peaq_b200_host_free_pinned(void* ptr) {
 
 double peaq_b200_engine_last_ms(const peaq_b200_engine* h, int which) {
   const Engine* e = reinterpret_cast<const Engine*>(h);
-  if (!e || which < 0 || which > 4) return -1.;
+  if (!e || which < 0 || which > 6) return -1.;
+  if (which == 4) return e->ms[7] + e->ms[5] + e->ms[6];
   return e->ms[which];
 }
 

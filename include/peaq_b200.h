@@ -105,7 +105,9 @@ int peaq_b200_host_free_pinned(void *ptr);
 
 /* Timing and accounting of the engine's last run_batch (CUDA events on the
  * engine's stream).  which: 0 whole batch, 1 frame kernel(s), 2 scan
- * kernel(s), 3 host->device copies, 4 filter-bank kernels.  Milliseconds. */
+ * kernel(s), 3 host->device copies, 4 all filter-bank-clock kernels, 5 of
+ * those the filter bank proper (fb_bank_rec_kernel), 6 the spreading and
+ * 192-sample-clock scan kernels.  Milliseconds. */
 double peaq_b200_engine_last_ms(const peaq_b200_engine *e, int which);
 /* kernels launched by this engine since creation */
 uint64_t peaq_b200_engine_launch_count(const peaq_b200_engine *e);

@@ -22,7 +22,7 @@ cap() {  # kernel-regex advanced skip name
 }
 cap fft_frames_kernel 0 1 fft_frames
 cap scan_basic_kernel 0 1 scan_basic
-cap fb_bank_kernel 1 1 fb_bank
+cap fb_bank_rec_kernel 1 1 fb_bank_rec
 cap fb_spread_kernel 1 1 fb_spread
 cap fb_scan_kernel 1 1 fb_scan
 cap fb_hp_kernel 1 1 fb_hp

@@ -417,3 +417,37 @@ def test_session_tiny_buffers_and_midstream_reads(advanced):
     np.testing.assert_allclose(res["movs"], want["movs"], rtol=MOV_RTOL, atol=1e-9, equal_nan=True)
     assert res["frames_fft"] == want["frames_fft"] and res["frames_fb"] == want["frames_fb"]
     p.close()
+
+
+def test_filter_bank_recursion_against_direct_fir():
+    """the sliding-window-DFT form of the 40 filters (fb_bank_rec_kernel) against
+    the polyphase direct-FIR kernel (PEAQ_B200_FB_DIRECT=1, read once per
+    process, hence the subprocess): per-frame excitations and MOVs"""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import json, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import gstpeaq_b200 as G
+from signals import synth_pair
+ch = 2
+ref, test = synth_pair(77, 30000, ch)
+e = G.Engine(0, advanced=True)
+e.keep_records(True)
+out = e.run_host(ref, test, ch)
+exc, movs = e.fb_debug(1, ch)
+print(json.dumps({"movs": out["movs"][0][:5].tolist(), "odg": float(out["odg"][0]),
+                  "exc": np.asarray(exc[0]).ravel().tolist()}))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for direct in ("0", "1"):
+        env = dict(os.environ, PEAQ_B200_FB_DIRECT=direct)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[direct] = json.loads(p.stdout.strip().splitlines()[-1])
+    a, b = res["0"], res["1"]
+    np.testing.assert_allclose(a["exc"], b["exc"], rtol=4e-9)
+    np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9, atol=1e-12)
+    assert abs(a["odg"] - b["odg"]) < 1e-9
