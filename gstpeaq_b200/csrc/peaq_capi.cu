@@ -541,14 +541,31 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     // host input: sub-batches of pairs are staged through two device slots; the
     // H2D copy of sub-batch i+1 (copy stream) overlaps the kernels of sub-batch i
     const size_t stride = n_pairs > 1 ? b->pair_stride : (size_t)max_n * C;
-    const size_t slot_budget = (size_t)3 << 28;   // floats per staging buffer (3 GiB)
-    int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, slot_budget / std::max<size_t>(stride, 1)));
-    if (per > 592 && n_pairs > 592) per = 592;    // 4 scan CTAs per SM and still several sub-batches
+    const size_t slot_budget = (size_t)1 << 30;   // floats per staging buffer (4 GiB)
+    const int per_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, slot_budget / std::max<size_t>(stride, 1)));
+    // Sub-batch sizes.  Basic mode is bound by the copies (16 KB of PCM per frame against
+    // ~100 ns of kernels), so the job takes all copies plus the kernels of the LAST sub-batch:
+    // small, equal sub-batches (one wave of scan CTAs).  Advanced mode is bound by the kernels,
+    // so it takes the FIRST copy plus all kernels: a small first sub-batch, then large ones (the
+    // DC-reject scan costs the same 25 ms per 10 s of audio whatever the sub-batch holds).
+    std::vector<int> sizes;
+    {
+      int left = n_pairs;
+      if (e->advanced && left > 256) {
+        sizes.push_back(std::min(per_max, 128));
+        left -= sizes.back();
+      }
+      const int per = std::min(per_max, e->advanced ? 1024 : 296);
+      while (left > 0) {
+        sizes.push_back(std::min(per, left));
+        left -= sizes.back();
+      }
+    }
     PairResult* d_all = nullptr;
     PEAQ_CUDA(cudaMalloc(&d_all, (size_t)n_pairs * sizeof(PairResult)));
-    int i = 0;
-    for (int p0 = 0; p0 < n_pairs; p0 += per, i++) {
-      const int np = std::min(per, n_pairs - p0);
+    int p0 = 0;
+    for (int i = 0; i < (int)sizes.size(); p0 += sizes[i], i++) {
+      const int np = sizes[i];
       const int slot = i & 1;
       const size_t floats = (size_t)(np - 1) * stride + (size_t)max_n * C;
       if (i >= 2) PEAQ_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_freed[slot], 0));
