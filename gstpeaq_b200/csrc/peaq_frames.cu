@@ -522,24 +522,41 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   }
   __syncthreads();   // staged PCM consumed: the buffers become FFT work space
 
-  // ---- phase 2: window, scatter into FFT order; energy; largest |x| for the threshold ----
+  // ---- phase 2: window, first FFT pass, scatter into FFT order; energy; largest |x| ----
   double2* z = reinterpret_cast<double2*>(work);
   {
     const int slot_t = fft_slot_rt<10>(t);
     float amax = 0.f;
+    // The thread's 16 points are n = t + 64 j + 256 m: for fixed j the four m are exactly the
+    // inputs of one butterfly of the FIRST radix-4 pass (top digit of n = lowest digit of the
+    // digit-reversed position, no twiddles), so that pass happens here in registers and the
+    // results go straight to the positions the scatter would have filled.
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int n = t + 64 * u;
-      const float x0 = xs0[u], x1 = xs1[u];
-      const double2 h = *reinterpret_cast<const double2*>(&T->hann[2 * n]);
-      z[slot_t ^ fft_slot<10>(64 * u)] = make_double2(h.x * x0, h.y * x1);
-      if (u >= 8) {   // samples 1024..2047: float products, double accumulation (fftearmodel.c:508-511)
-        energy += (double)(x0 * x0);
-        energy += (double)(x1 * x1);
+    for (int j = 0; j < 4; j++) {
+      double2 a[4];
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const int u = j + 4 * m;
+        const int n = t + 64 * u;
+        const float x0 = xs0[u], x1 = xs1[u];
+        const double2 h = *reinterpret_cast<const double2*>(&T->hann[2 * n]);
+        a[m] = make_double2(h.x * x0, h.y * x1);
+        if (u >= 8) {   // samples 1024..2047: float products, double accumulation (fftearmodel.c:508-511)
+          energy += (double)(x0 * x0);
+          energy += (double)(x1 * x1);
+        }
+        // sample 0 never enters a tested window (gstpeaq.c:1088-1096: windows end at i >= 5)
+        if (n > 0) amax = fmaxf(amax, fabsf(x0));
+        amax = fmaxf(amax, fabsf(x1));
       }
-      // sample 0 never enters a tested window (gstpeaq.c:1088-1096: windows end at i >= 5)
-      if (n > 0) amax = fmaxf(amax, fabsf(x0));
-      amax = fmaxf(amax, fabsf(x1));
+      const double2 t0 = make_double2(a[0].x + a[2].x, a[0].y + a[2].y);
+      const double2 t1 = make_double2(a[0].x - a[2].x, a[0].y - a[2].y);
+      const double2 t2 = make_double2(a[1].x + a[3].x, a[1].y + a[3].y);
+      const double2 t3 = make_double2(a[1].y - a[3].y, a[3].x - a[1].x);   // -i (a1 - a3)
+      z[slot_t ^ fft_slot<10>(64 * j)] = make_double2(t0.x + t2.x, t0.y + t2.y);
+      z[slot_t ^ fft_slot<10>(64 * (j + 4))] = make_double2(t1.x + t3.x, t1.y + t3.y);
+      z[slot_t ^ fft_slot<10>(64 * (j + 8))] = make_double2(t0.x - t2.x, t0.y - t2.y);
+      z[slot_t ^ fft_slot<10>(64 * (j + 12))] = make_double2(t1.x - t3.x, t1.y - t3.y);
     }
     energy = warp_sum(energy);
 #pragma unroll
@@ -560,7 +577,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   __syncthreads();   // twiddles loaded, mail published, scatter of both halves complete
 
   // ---- 2048-point real FFT by the stream's 64 threads; power spectrum into registers ----
-  group_fft<10, 64, StreamSync>(z, tw, t, StreamSync{1 + stream});
+  FftPasses<10, 4, 64, StreamSync>::run(z, tw, t, StreamSync{1 + stream});   // passes 2..5
   double pv[16], p_nyq = 0.;
   {
     const double lf = T->level_factor_fft;
