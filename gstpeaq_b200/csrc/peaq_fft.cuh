@@ -102,10 +102,13 @@ __device__ __forceinline__ void fft_pass4(double2* z, const double2* __restrict_
   const int base = LQ <= NT ? ((t - k_t) << 2) + k_t : t;
   const int sb = fft_swz(base);
   double2 w1, w2, w3;
+  // w^2 and w^3 are computed from w instead of loaded: the strided table reads conflict in the
+  // banks (they were half of all excess shared-memory wavefronts of the frame kernel) and the
+  // FP64 pipe has room; |w^2 - table| ~ 2e-16, irrelevant for the transform's accuracy
   if (LQ > 1 && LQ <= NT) {   // twiddles depend on the thread only
     w1 = tw[k_t * TS];
-    w2 = tw[2 * k_t * TS];
-    w3 = fft_tw(tw, 3 * k_t * TS);
+    w2 = cmul(w1, w1);
+    w3 = cmul(w2, w1);
   }
 #pragma unroll
   for (int u = 0; u < N / (4 * NT); u++) {
@@ -116,8 +119,8 @@ __device__ __forceinline__ void fft_pass4(double2* z, const double2* __restrict_
     if (LQ > NT) {
       const int k = t | (NT * (u % (LQ / NT)));
       w1 = tw[k * TS];
-      w2 = tw[2 * k * TS];
-      w3 = fft_tw(tw, 3 * k * TS);
+      w2 = cmul(w1, w1);
+      w3 = cmul(w2, w1);
     }
     if (LQ > 1) {
       a1 = cmul(a1, w1);
