@@ -578,39 +578,44 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
 
   // ---- 2048-point real FFT by the stream's 64 threads; power spectrum into registers ----
   FftPasses<10, 4, 64, StreamSync>::run(z, tw, t, StreamSync{1 + stream});   // passes 2..5
-  double pv[16], p_nyq = 0.;
+  // Z[k] and Z[1024-k] give X[k] = E + P and X[1024-k] = conj(E - P) (E, O the even/odd parts,
+  // P = O w^k), so one pair of loads and one twiddle product serve two bins: register u < 8
+  // holds bin t + 64 u, register 8 + u its mirror 1024 - (t + 64 u); bin 512 (its own mirror)
+  // is an extra of thread 0.
+  double pv[16], p_mid = 0.;
+  auto bin_of = [&](int u) { return u < 8 ? t + 64 * u : 1024 - (t + 64 * (u - 8)); };
   {
     const double lf = T->level_factor_fft;
     const int sw = fft_swz(t);
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
+    for (int u = 0; u < 8; u++) {
       const int k = t + 64 * u;
       const double2 p = z[sw ^ fft_swz(64 * u)];
       const double2 q = z[fft_swz((1024 - k) & 1023)];
       const double er = 0.5 * (p.x + q.x), ei = 0.5 * (p.y - q.y);
       const double orr = 0.5 * (p.y + q.y), oi = -0.5 * (p.x - q.x);
       const double wr = T->tw2048[k].x, wi = T->tw2048[k].y;
-      const double xr = er + (orr * wr - oi * wi);
-      const double xi = ei + (orr * wi + oi * wr);
+      const double pr = orr * wr - oi * wi, pi = orr * wi + oi * wr;
+      const double xr = er + pr, xi = ei + pi;
+      const double yr = er - pr, yi = ei - pi;
       pv[u] = (xr * xr + xi * xi) * lf;   // fftearmodel.c:464-466
+      pv[8 + u] = (yr * yr + yi * yi) * lf;
     }
     if (t == 0) {
-      // bin 1024: X = Re Z[0] - Im Z[0] through the same formula
-      const double2 p = z[fft_swz(0)];
-      const double wr = T->tw2048[1024].x, wi = T->tw2048[1024].y;
-      const double xr = p.x + (p.y * wr - 0. * wi);
-      const double xi = 0. + (p.y * wi + 0. * wr);
-      p_nyq = (xr * xr + xi * xi) * lf;
+      const double2 p = z[fft_swz(512)];   // E = (Re, 0), O = (Im, 0), w^512 = -i
+      const double wr = T->tw2048[512].x, wi = T->tw2048[512].y;
+      const double xr = p.x + p.y * wr, xi = p.y * wi;
+      p_mid = (xr * xr + xi * xi) * lf;
     }
   }
-  (void)p_nyq;   // bin 1024 is outside everything the path reads (see kSpecBins)
 
   double* rec = records + ((size_t)pair * n_chunk_frames + chunk_frame) * L.stride;
 
   // ---- bandwidth on the register-held spectrum (movs.c:783-803) ----------------------
   if (side == 1) {
-    double thr = pv[15];   // bin 960 + t: a start value inside the range 921..1023
-    if (896 + t >= 921 && pv[14] >= thr) thr = pv[14];
+    // bins 921..1023: register 8 (bin 1024 - t, t >= 1) and register 9 (bin 960 - t, t <= 39)
+    double thr = t >= 1 ? pv[8] : pv[9];
+    if (t >= 1 && t <= 39 && pv[9] >= thr) thr = pv[9];
     thr = warp_max_nonan(thr);
     if (lane == 0) mail->thr_part[chan][half] = thr;
   }
@@ -623,10 +628,11 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   if (side == 0) {
     int bw_ref = 0;
 #pragma unroll
-    for (int u = 0; u < 15; u++) {
-      const int k = t + 64 * u;
-      if (k < 921 && pv[u] > 10. * zero_thr) bw_ref = k + 1;
+    for (int u = 0; u < 16; u++) {
+      const int k = bin_of(u);
+      if (k < 921 && pv[u] > 10. * zero_thr) bw_ref = max(bw_ref, k + 1);
     }
+    if (t == 0 && p_mid > 10. * zero_thr) bw_ref = max(bw_ref, 513);
     bw_ref = warp_max_int(bw_ref);
     if (lane == 0) mail->bw_ref_part[chan][half] = bw_ref;
   }
@@ -636,10 +642,11 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     int bw_test = 0;
     if (bw_ref > 346) {
 #pragma unroll
-      for (int u = 0; u < 15; u++) {
-        const int k = t + 64 * u;
-        if (k < bw_ref && pv[u] >= 3.16227766016838 * zero_thr) bw_test = k + 1;
+      for (int u = 0; u < 16; u++) {
+        const int k = bin_of(u);
+        if (k < bw_ref && pv[u] >= 3.16227766016838 * zero_thr) bw_test = max(bw_test, k + 1);
       }
+      if (t == 0 && 512 < bw_ref && p_mid >= 3.16227766016838 * zero_thr) bw_test = max(bw_test, 513);
       bw_test = warp_max_int(bw_test);
     }
     if (lane == 0) mail->bw_test_part[chan][half] = bw_test;
@@ -648,10 +655,11 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   // ---- weighted power spectrum back into the (now free) FFT buffer ----------------
   double* spec = work;
 #pragma unroll
-  for (int u = 0; u < 13; u++) {
-    const int k = t + 64 * u;
+  for (int u = 0; u < 16; u++) {
+    const int k = bin_of(u);
     if (k < kSpecBins) spec[k] = pv[u] * T->earw2[k];   // fftearmodel.c:470-472
   }
+  if (t == 0) spec[512] = p_mid * T->earw2[512];
   chan_sync(chan);   // both spectra of the channel (and bw_test_part) visible
 
   double* buf_ref = smem + kTwDoubles + (2 * chan) * kWorkDoubles;
