@@ -451,3 +451,27 @@ print(json.dumps({"movs": out["movs"][0][:5].tolist(), "odg": float(out["odg"][0
     np.testing.assert_allclose(a["exc"], b["exc"], rtol=4e-9)
     np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9, atol=1e-12)
     assert abs(a["odg"] - b["odg"]) < 1e-9
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_unaligned_mono_batch_matches_oracle(advanced):
+    """mono pairs at an odd stride: every pair but the first starts off the 16-byte grid, so the
+    frame kernel's guarded staging path (no TMA) and the scalar loads of the filter-bank input
+    are the ones that run"""
+    ch = 1
+    lengths = [30001, 29999, 30001]
+    stride = 30001
+    ref = np.zeros((len(lengths), stride), np.float32)
+    test = np.zeros_like(ref)
+    for p, n in enumerate(lengths):
+        r, t = synth_pair(300 + p, n, ch)
+        ref[p, :n] = r
+        test[p, :n] = t
+    e = G.Engine(0, advanced=advanced)
+    try:
+        out = e.run_host(ref, test, ch, n_samples=np.array(lengths, np.uint64))
+    finally:
+        e.close()
+    for p, n in enumerate(lengths):
+        want = H.oracle_run_pair(ref[p, :n], test[p, :n], ch, advanced=advanced)
+        check_result(out[p], want, "mono pair %d len %d adv %d" % (p, n, advanced))
