@@ -6,11 +6,15 @@
 //   FB1 fb_hp_kernel      playback-level scaling + DC-reject filter, two cascaded
 //                         biquads (fbearmodel.c:289-303): sequential in time, one
 //                         thread per stream, state carried between chunks
-//   FB2 fb_bank_kernel    40 complex FIR filters of 52..1456 taps evaluated every
-//                         32 samples (apply_filter_bank, fbearmodel.c:398-435)
+//   FB2 fb_bank_rec_kernel  the 40 complex FIR filters of 52..1456 taps, evaluated every
+//                         32 samples (apply_filter_bank, fbearmodel.c:398-435), as
+//                         sliding windowed DFTs: 384 FMAs per band and sub-step whatever
+//                         the filter length (see the comment at the kernel)
+//       fb_bank_kernel    the same filters as polyphase direct FIRs (2 (N - 1) FMAs per
+//                         band and sub-step); the engine's cross-check, selected with
+//                         PEAQ_B200_FB_DIRECT=1 (tests/test_gpu_parity.py compares the two)
 //
-// FB2 is the contraction-shaped stage (2.8 M FMA per stereo PEAQ frame).  It is
-// computed as 32 polyphase sub-convolutions: with delay d = 32 q + j,
+// The direct kernel computes 32 polyphase sub-convolutions: with delay d = 32 q + j,
 //   out_b[s] = sum_j sum_q G_b[32 q + j] * x[32 (s - q) - j]
 // so for a fixed phase j consecutive outputs slide over the same decimated
 // input sequence.  Each lane owns R = 7 consecutive outputs and keeps the sliding
