@@ -144,6 +144,11 @@ struct Engine {
   size_t hp_cap = 0;
   double* d_hp_state = nullptr;
   size_t hp_state_cap = 0;
+  // whole-item mode of the DC-reject scan: its own high-priority stream, so that the (chain
+  // bound, few-thread) scan of the whole batch hides underneath the frame kernel
+  cudaStream_t hp_stream = nullptr;
+  cudaEvent_t ev_hp_ready = nullptr, ev_hp_done = nullptr;
+  size_t hp_whole_budget_bytes = (size_t)72 << 30;
   double* d_fbout = nullptr;
   size_t fbout_cap = 0;
   double* d_fbenergy = nullptr;   // rectified sub-step energies [stream][sub-step][band]
@@ -174,6 +179,13 @@ struct Engine {
     PEAQ_CUDA(cudaSetDevice(device));
     PEAQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     PEAQ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    {
+      int prio_lo = 0, prio_hi = 0;
+      PEAQ_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      PEAQ_CUDA(cudaStreamCreateWithPriority(&hp_stream, cudaStreamNonBlocking, prio_hi));
+      PEAQ_CUDA(cudaEventCreateWithFlags(&ev_hp_ready, cudaEventDisableTiming));
+      PEAQ_CUDA(cudaEventCreateWithFlags(&ev_hp_done, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; i++) {
       PEAQ_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
       PEAQ_CUDA(cudaEventCreateWithFlags(&ev_freed[i], cudaEventDisableTiming));
@@ -191,12 +203,17 @@ struct Engine {
       const long mb = std::atol(env);
       if (mb > 0) fb_budget_bytes = (size_t)mb << 20;
     }
+    if (const char* env = std::getenv("PEAQ_B200_HP_WHOLE_BUDGET_MB")) {
+      const long mb = std::atol(env);
+      if (mb >= 0) hp_whole_budget_bytes = (size_t)mb << 20;
+    }
     return 0;
   }
 
   void destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    if (hp_stream) cudaStreamSynchronize(hp_stream);
     for (auto& e : events) {
       cudaEventDestroy(e.a);
       cudaEventDestroy(e.b);
@@ -213,6 +230,9 @@ struct Engine {
       if (ev_freed[i]) cudaEventDestroy(ev_freed[i]);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_hp_ready) cudaEventDestroy(ev_hp_ready);
+    if (ev_hp_done) cudaEventDestroy(ev_hp_done);
+    if (hp_stream) cudaStreamDestroy(hp_stream);
     cudaFree(d_hp);
     cudaFree(d_hp_state);
     cudaFree(d_fbout);
@@ -425,7 +445,17 @@ struct Engine {
         else if (chunk >= 32) chunk -= chunk % 32;
       }
       if (keep_records) chunk = std::max<unsigned>(max_fb_frames, 1);
-      const size_t hp_stride = kFbHist + chunk * kFbFrame;
+      // Whole-item mode (fresh batches whose filtered signal and FFT-clock records fit): the
+      // DC-reject scan of ALL frames goes to its own stream first and the frame kernel runs
+      // meanwhile -- the scan keeps a few warps busy for 25 ms per 10 s of audio whatever the
+      // batch, the frame kernel leaves just enough registers per SM for it.  Results are the
+      // same either way (same kernels, same arithmetic).
+      const size_t rec_bytes_all = (size_t)n_pairs * std::max<unsigned>(max_frames, 1) * L.stride * sizeof(double);
+      const bool whole = reset_state && !keep_records && max_fb_frames > 0 && d_ref_fb == nullptr &&
+                         (size_t)n_streams * (kFbHist + (size_t)max_fb_frames * kFbFrame) * sizeof(double) <=
+                             hp_whole_budget_bytes &&
+                         rec_bytes_all <= record_budget_bytes;
+      const size_t hp_stride = kFbHist + (whole ? (size_t)max_fb_frames : chunk) * kFbFrame;
       if ((rc = ensure(&d_hp, &hp_cap, (size_t)n_streams * hp_stride))) return rc;
       if ((size_t)n_streams * kHpStateDoubles > hp_state_cap && !reset_state)
         return fail(PEAQ_B200_ERR_INVALID, "filter state would be lost on growth");
@@ -443,27 +473,50 @@ struct Engine {
         last_fbdbg_doubles = need;
         last_fb_frames = (unsigned)chunk;
       }
+      if (whole) {
+        PEAQ_CUDA(cudaEventRecord(ev_hp_ready, stream));          // plans uploaded, PCM resident, state fresh
+        PEAQ_CUDA(cudaStreamWaitEvent(hp_stream, ev_hp_ready, 0));
+        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, 0ull, max_fb_frames * kFbFrame, d_hp, hp_stride,
+                               d_hp_state, true, hp_stream));
+        PEAQ_CUDA(cudaEventRecord(ev_hp_done, hp_stream));
+        launches++;
+        // the frame kernel of the whole FFT clock, underneath which the scan runs
+        if ((rc = ensure(&d_records, &records_cap, (size_t)n_pairs * std::max<unsigned>(max_frames, 1) * L.stride)))
+          return rc;
+        if (max_frames > 0) {
+          if ((rc = timer_begin(1))) return rc;
+          PEAQ_CUDA(launch_fft_frames(d_tables, pcm, n_pairs, 0, max_frames, d_records, L, B, advanced, stream));
+          launches++;
+          if ((rc = timer_end())) return rc;
+        }
+        PEAQ_CUDA(cudaStreamWaitEvent(stream, ev_hp_done, 0));
+      }
       unsigned first = 0;
       while (first < max_fb_frames) {
         const unsigned n = (unsigned)std::min<size_t>(chunk, max_fb_frames - first);
         const unsigned n_sub = n * 6, samples = n * kFbFrame;
         if ((rc = timer_begin(7))) return rc;
         PEAQ_CUDA(launch_fb_flags(pcm_fb, n_pairs, first, n, d_fbflags, stream));
-        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
-                               hp_stride, d_hp_state, first == 0 && reset_state, stream));
+        if (!whole) {
+          PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
+                                 hp_stride, d_hp_state, first == 0 && reset_state, stream));
+        }
         if ((rc = timer_end())) return rc;
         // PEAQ_B200_FB_DIRECT=1: all 40 filters as direct FIRs (development aid / cross-check)
         static const bool fb_direct = std::getenv("PEAQ_B200_FB_DIRECT") && std::atoi(std::getenv("PEAQ_B200_FB_DIRECT"));
         if ((rc = timer_begin(5))) return rc;
-        PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp, hp_stride, n_streams, n_sub, d_fbout, d_hp_state,
-                                 first == 0 && reset_state, fb_direct, stream));
+        // whole-item mode: the chunk starts `first` frames into the filtered signal, its FIR
+        // history is simply what precedes it there
+        PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp + (whole ? (size_t)first * kFbFrame : 0), hp_stride,
+                                 n_streams, n_sub, d_fbout, d_hp_state, first == 0 && reset_state, fb_direct,
+                                 stream));
         if ((rc = timer_end())) return rc;
         if ((rc = timer_begin(6))) return rc;
         PEAQ_CUDA(launch_fb_spread(d_tables, d_fbout, n_sub, pcm_fb.n_frames, first, d_state, A, d_fbenergy,
                                    n_pairs, stream));
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, n_sub, d_fbflags, pcm_fb.n_frames, first, n, d_state, A,
                                  dbg, n_pairs, stream));
-        launches += 5;
+        launches += whole ? 4 : 5;
         if ((rc = timer_end())) return rc;
         first += n;
       }
@@ -474,11 +527,21 @@ struct Engine {
         launches++;
       }
       // ---- FFT clock; its epilogue combines all five MOVs ---------------------------
-      rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first_f, unsigned n) {
-        return launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, first_f, n, d_state, A, d_res,
-                                   n_pairs, stream);
-      });
-      if (rc) return rc;
+      if (whole) {
+        if ((rc = timer_begin(2))) return rc;
+        PEAQ_CUDA(launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, 0, max_frames, d_state, A, d_res,
+                                      n_pairs, stream));
+        launches++;
+        if ((rc = timer_end())) return rc;
+        last_layout = L;
+        last_records_doubles = 0;
+      } else {
+        rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first_f, unsigned n) {
+          return launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, first_f, n, d_state, A, d_res,
+                                     n_pairs, stream);
+        });
+        if (rc) return rc;
+      }
     }
 
     if (!blocking) return 0;
