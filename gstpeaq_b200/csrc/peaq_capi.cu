@@ -451,7 +451,10 @@ struct Engine {
       // batch, the frame kernel leaves just enough registers per SM for it.  Results are the
       // same either way (same kernels, same arithmetic).
       const size_t rec_bytes_all = (size_t)n_pairs * std::max<unsigned>(max_frames, 1) * L.stride * sizeof(double);
+      // (beyond ~2 scan CTAs per SM the scan starts to displace frame-kernel CTAs and the
+      // overlap stops paying: 4096 pairs measured 878 ms against 870 ms without it)
       const bool whole = reset_state && !keep_records && max_fb_frames > 0 && d_ref_fb == nullptr &&
+                         n_streams <= 8192 &&
                          (size_t)n_streams * (kFbHist + (size_t)max_fb_frames * kFbFrame) * sizeof(double) <=
                              hp_whole_budget_bytes &&
                          rec_bytes_all <= record_budget_bytes;
@@ -609,12 +612,12 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     // Sub-batch sizes.  Basic mode is bound by the copies (16 KB of PCM per frame against
     // ~100 ns of kernels), so the job takes all copies plus the kernels of the LAST sub-batch:
     // small, equal sub-batches (one wave of scan CTAs).  Advanced mode is bound by the kernels,
-    // so it takes the FIRST copy plus all kernels: a small first sub-batch, then large ones (the
-    // DC-reject scan costs the same 25 ms per 10 s of audio whatever the sub-batch holds).
+    // so it takes the FIRST copy plus all kernels: a small first sub-batch, then large ones.
     std::vector<int> sizes;
     {
       int left = n_pairs;
       if (e->advanced && left > 256) {
+        // measured best among 128 / 256-doubling / 640 first (1068 / 1092 / 1108 ms per 4096 pairs)
         sizes.push_back(std::min(per_max, 128));
         left -= sizes.back();
       }
