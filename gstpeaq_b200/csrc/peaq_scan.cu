@@ -207,6 +207,18 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
     Eft = a_ear * Eft + (1. - a_ear) * E2t;
     const double Et = Eft > E2t ? Eft : E2t;
 
+    // modulation (modpatt.c:234-250): needs nothing but the unsmeared excitations, so it sits in
+    // this phase, where its exp/log chain overlaps the detection-probability chain below
+    const double Lr = exp(0.3 * log(E2r)), Lt = exp(0.3 * log(E2t));
+    fd_r = a_proc * fd_r + (1 - a_proc) * (deriv_factor * fabs(Lr - prev_r));
+    fl_r = a_proc * fl_r + (1. - a_proc) * Lr;
+    const double mod_r = fd_r / (1. + fl_r / 0.3);
+    prev_r = Lr;
+    fd_t = a_proc * fd_t + (1 - a_proc) * (deriv_factor * fabs(Lt - prev_t));
+    fl_t = a_proc * fl_t + (1. - a_proc) * Lt;
+    const double mod_t = fd_t / (1. + fl_t / 0.3);
+    prev_t = Lt;
+
     // level adaptation, first part (leveladapter.c:262-277)
     Rf = a_proc * Rf + (1 - a_proc) * Er;
     Tf = a_proc * Tf + (1 - a_proc) * Et;
@@ -290,17 +302,6 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
     pcr = a_proc * pcr + (1 - a_proc) * ra_r;
     pct = a_proc * pct + (1 - a_proc) * ra_t;
     const double adr = lcr * pcr, adt = lct * pct;
-
-    // modulation (modpatt.c:234-250)
-    const double Lr = exp(0.3 * log(E2r)), Lt = exp(0.3 * log(E2t));
-    fd_r = a_proc * fd_r + (1 - a_proc) * (deriv_factor * fabs(Lr - prev_r));
-    fl_r = a_proc * fl_r + (1. - a_proc) * Lr;
-    const double mod_r = fd_r / (1. + fl_r / 0.3);
-    prev_r = Lr;
-    fd_t = a_proc * fd_t + (1 - a_proc) * (deriv_factor * fabs(Lt - prev_t));
-    fl_t = a_proc * fl_t + (1. - a_proc) * Lt;
-    const double mod_t = fd_t / (1. + fl_t / 0.3);
-    prev_t = Lt;
 
     double r2[kRed2];
     // modulation difference terms (movs.c:226-242)
