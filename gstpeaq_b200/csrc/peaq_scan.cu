@@ -219,6 +219,25 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
     const double mod_t = fd_t / (1. + fl_t / 0.3);
     prev_t = Lt;
 
+    // everything below needs no other band or channel, so it runs here, alongside the
+    // detection-probability chain: modulation difference terms (movs.c:226-242), the
+    // modulation-only factor of the noise loudness (movs.c:725-738), the noise-to-mask
+    // ratio term (movs.c:1002-1011)
+    double r2[kRed2];
+    {
+      const double diff = fabs(mod_r - mod_t);
+      r2[0] = diff / (1. + mod_r);
+      const double w = mod_t >= mod_r ? 1. : .1;
+      r2[1] = w * diff / (0.01 + mod_r);
+      r2[2] = fl_r / (fl_r + 100. * in03);
+    }
+    const double sref = 0.15 * mod_r + 0.5;
+    const double stest = 0.15 * mod_t + 0.5;
+    const double nl_fac = exp(0.23 * log(in_noise / stest));
+    const double curr_nmr = nz / (Er / maskdiff);
+    r2[4] = curr_nmr;
+    double nmr_max = curr_nmr > 0. ? curr_nmr : 0.;
+
     // level adaptation, first part (leveladapter.c:262-277)
     Rf = a_proc * Rf + (1 - a_proc) * Er;
     Tf = a_proc * Tf + (1 - a_proc) * Et;
@@ -303,28 +322,13 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
     pct = a_proc * pct + (1 - a_proc) * ra_t;
     const double adr = lcr * pcr, adt = lct * pct;
 
-    double r2[kRed2];
-    // modulation difference terms (movs.c:226-242)
+    // noise loudness term (movs.c:725-738) with alpha 1.5, ThresFac 0.15, S0 0.5; the factor
+    // that only depends on the test modulation was prepared in front of barrier A
     {
-      const double diff = fabs(mod_r - mod_t);
-      r2[0] = diff / (1. + mod_r);
-      const double w = mod_t >= mod_r ? 1. : .1;
-      r2[1] = w * diff / (0.01 + mod_r);
-      r2[2] = fl_r / (fl_r + 100. * in03);
-    }
-    // noise loudness term (movs.c:725-738) with alpha 1.5, ThresFac 0.15, S0 0.5
-    {
-      const double sref = 0.15 * mod_r + 0.5;
-      const double stest = 0.15 * mod_t + 0.5;
       const double beta = exp(-1.5 * (adt - adr) / adr);
       const double d = stest * adt - sref * adr;
-      r2[3] = exp(0.23 * log(in_noise / stest)) *
-              (exp(0.23 * log(1. + (d > 0. ? d : 0.) / (in_noise + sref * adr * beta))) - 1.);
+      r2[3] = nl_fac * (exp(0.23 * log(1. + (d > 0. ? d : 0.) / (in_noise + sref * adr * beta))) - 1.);
     }
-    // noise-to-mask ratio term (movs.c:1002-1011)
-    const double curr_nmr = nz / (Er / maskdiff);
-    r2[4] = curr_nmr;
-    double nmr_max = curr_nmr > 0. ? curr_nmr : 0.;
     // binaural detection (movs.c:1261-1267), evaluated by channel 0's threads
     double one_minus_p = 1., qsteps = 0.;
     if (c == 0) {
