@@ -351,6 +351,20 @@ def our_arm(args):
                 "scan_kernel_ms_per_step": k2_ms / args.steps,
                 "kernel_share_of_step": dom_ms * args.steps / dev_ms,
                 "note": "FP64 latency/issue bound in practice (DESIGN.md 3); HBM fraction reported as the north star asks"}
+    # the binding resource next to it: the FP64 pipe, against a measured DFMA loop
+    try:
+        fp64_peak = float(L.peaq_b200_fp64_peak_tflops(local_rank))
+    except Exception:
+        fp64_peak = -1.0
+    if fp64_peak > 0:
+        roofline["fp64_peak_tflops_measured"] = fp64_peak
+        if MODE == "advanced":
+            # fb_bank_rec_kernel: 384 FMAs per band and 32-sample sub-step, 40 bands, 32 sub-steps
+            # and 4 streams per PEAQ frame
+            flop = 2.0 * 384 * 40 * 32 * 2 * CHANNELS * frames_rank
+            roofline["fp64_algorithmic_flop_per_launch_set"] = flop
+            roofline["fp64_achieved_tflops"] = flop / (dom_ms / 1e3) / 1e12
+            roofline["fp64_frac"] = roofline["fp64_achieved_tflops"] / fp64_peak
 
     # ---- CPU baseline (N = 1 only): bounded sample on the host cores ------------
     cpu = None

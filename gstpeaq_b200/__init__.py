@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "peaq_b200_session_create", "peaq_b200_session_destroy", "peaq_b200_session_set_advanced",
     "peaq_b200_session_set_playback_level", "peaq_b200_session_get_playback_level",
     "peaq_b200_session_set_channels", "peaq_b200_session_push", "peaq_b200_session_finish",
-    "peaq_b200_session_get_result",
+    "peaq_b200_session_get_result", "peaq_b200_fp64_peak_tflops",
 ]
 
 MOV_NAMES_BASIC = ["BandwidthRefB", "BandwidthTestB", "Total NMRB", "WinModDiff1B", "ADBB", "EHSB",
@@ -116,6 +116,8 @@ def load_library():
     L.peaq_b200_engine_last_ms.argtypes = [C.c_void_p, C.c_int]
     L.peaq_b200_engine_launch_count.restype = C.c_uint64
     L.peaq_b200_engine_launch_count.argtypes = [C.c_void_p]
+    L.peaq_b200_fp64_peak_tflops.restype = C.c_double
+    L.peaq_b200_fp64_peak_tflops.argtypes = [C.c_int]
     L.peaq_b200_engine_keep_records.argtypes = [C.c_void_p, C.c_int]
     L.peaq_b200_engine_record_layout.argtypes = [C.c_void_p, C.c_void_p]
     L.peaq_b200_engine_copy_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t,

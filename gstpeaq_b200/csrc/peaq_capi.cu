@@ -934,6 +934,50 @@ double peaq_b200_engine_last_ms(const peaq_b200_engine* h, int which) {
   return e->ms[which];
 }
 
+namespace {
+// 8 independent DFMA chains per thread: with >= 16 warps per scheduler the FP64 pipe is the only limit
+__global__ void fp64_peak_kernel(double* out, int iters, double b, double c) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = (double)(threadIdx.x + k);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = fma(a[k], b, c);
+  }
+  double s = 0.;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+double peaq_b200_fp64_peak_tflops(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double* d = nullptr;
+  if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = -1.;
+  for (int rep = 0; rep < 4; rep++) {   // first repetition warms up
+    cudaEventRecord(a);
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double tf = 2. * 8. * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  return best;
+}
+
 uint64_t peaq_b200_engine_launch_count(const peaq_b200_engine* h) {
   const Engine* e = reinterpret_cast<const Engine*>(h);
   return e ? e->launches : 0;

@@ -111,6 +111,10 @@ int peaq_b200_host_free_pinned(void *ptr);
 double peaq_b200_engine_last_ms(const peaq_b200_engine *e, int which);
 /* kernels launched by this engine since creation */
 uint64_t peaq_b200_engine_launch_count(const peaq_b200_engine *e);
+/* Measured FP64 FMA throughput of the device in TFLOP/s (a register-resident DFMA loop on every
+ * SM, CUDA-event timed; < 0 on error).  The path is FP64 bound: this is the denominator the
+ * kernels' achieved FMA rates are quoted against, next to the HBM roofline. */
+double peaq_b200_fp64_peak_tflops(int device);
 
 /* Debug taps for the parity tests: per-frame records of the last run_batch
  * (only kept when enabled before the run).  Layout: see
