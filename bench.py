@@ -292,7 +292,8 @@ def our_arm(args):
         e2e_pairs = count
         try:
             import psutil
-            avail = psutil.virtual_memory().available
+            # every rank of the node pins its own buffers at the same time
+            avail = psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
             while e2e_pairs > 64 and 2 * e2e_pairs * stride * 4 * 1.3 > avail:
                 e2e_pairs //= 2
         except Exception:
