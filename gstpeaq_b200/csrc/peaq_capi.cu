@@ -1026,6 +1026,31 @@ int peaq_b200_table(int advanced, double playback_level, int model, int which, d
   build_tables(tp, advanced != 0, playback_level);
   struct Guard { DeviceTables* p; ~Guard() { delete p; } } guard{tp};
   const DeviceTables& t = *tp;
+  if (model == 2) {
+    // filter-bank tables of band `which`: N, D, the recursion coefficients [32][6] complex and
+    // rotations [3][6] complex (fb_bank_rec_kernel), then the reference-form taps re[0..N/2],
+    // im[0..N/2] (fbearmodel.c:213-220) -- up to 1880 doubles
+    if (which < 0 || which >= kFbBands) return fail(PEAQ_B200_ERR_INVALID, "no such band");
+    const int N = t.fb_len[which];
+    int n = 0;
+    out[n++] = N;
+    out[n++] = 1 + (kFbBuf - N) / 2;
+    if (which < kFbRecBands) {
+      for (int k = 0; k < 32; k++)
+        for (int f = 0; f < 6; f++) {
+          out[n++] = t.fb_rec_ph[which][k][f].x;
+          out[n++] = t.fb_rec_ph[which][k][f].y;
+        }
+      for (int f = 0; f < 3; f++)
+        for (int i = 0; i < kFbRecGroup; i++) {
+          out[n++] = t.fb_rec_rpow[which][f][i].x;
+          out[n++] = t.fb_rec_rpow[which][f][i].y;
+        }
+    }
+    for (int i = 0; i <= N / 2; i++) out[n++] = t.fb_h_re[t.fb_tap_offset[which] + i];
+    for (int i = 0; i <= N / 2; i++) out[n++] = t.fb_h_im[t.fb_tap_offset[which] + i];
+    return n;
+  }
   const BandTables& b = model ? t.fb : t.fft;
   for (int i = 0; i < b.B; i++) {
     double v;

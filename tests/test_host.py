@@ -87,3 +87,31 @@ def test_engine_tables_match_oracle_tables():
                 if want.size:
                     np.testing.assert_allclose(got, want, rtol=2e-15, atol=0,
                                                err_msg=str((advanced, model, which)))
+
+
+def test_filter_bank_recursion_tables_reproduce_the_taps():
+    """host-only check of the sliding-DFT form of the filter bank (fb_bank_rec_kernel): for every
+    band the three coefficient sets sum to the reference's taps, the removal coefficients are the
+    entry coefficients times -e^{jwN}, and the rotations are unit-modulus powers"""
+    import gstpeaq_b200 as G
+    for band in range(40):
+        t = G.fb_filter_tables(band)
+        N, ph, rp, h = t["N"], t["ph"], t["rpow"], t["h"]
+        scale = np.abs(ph).max()   # the three terms cancel (2 - 1 - 1) near the window's edge
+        k = np.arange(32)
+        # full-length taps: even / odd symmetry about N/2 (fbearmodel.c:418-425)
+        h = np.concatenate([h, np.conj(h[-2::-1])])
+        # sum_f P_f[k] = (Wt/N)(2 - e^{jdk} - e^{-jdk}) e^{jw(k - N/2)} = h[k]   (N >= 52 > 2 * 31)
+        # (the reference's taps carry the rounding of their cosine arguments, ~1700 rad: 2e-13 relative)
+        np.testing.assert_allclose(ph[:, :3].sum(axis=1), h[k], rtol=1e-12, atol=2e-15 * scale)
+        # Q_f[k] = -c P_f[k] with one unit-modulus c per band
+        c = -ph[:, 3:] / ph[:, :3]
+        np.testing.assert_allclose(np.abs(c), 1.0, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(c, c[1, 0], rtol=0, atol=1e-12)
+        # rotations: |r| = 1, r_f^(i+1); and P_f[k+1] / P_f[k] = e^{j w_f} = r_f^(1/32)
+        np.testing.assert_allclose(np.abs(rp), 1.0, rtol=0, atol=1e-15)
+        for f in range(3):
+            np.testing.assert_allclose(rp[f], rp[f, 0] ** np.arange(1, 7), rtol=0, atol=1e-14)
+            step = ph[1:, f] / ph[:-1, f]
+            np.testing.assert_allclose(step ** 32, rp[f, 0], rtol=0, atol=1e-12)
+        assert t["D"] == 1 + (1456 - N) // 2
