@@ -258,9 +258,19 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
   }
 }
 
+// barrier of the two warps of one stream (ids 1..4), of the four warps of one channel
+// (ids 5, 6) and the arrive/wait pair that guards the ref buffer (ids 7, 8)
+struct StreamSync {
+  int id;
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+};
+
 // Error harmonic structure of one channel (peaq_mov_ehs, movs.c:1383-1441),
-// run by one warp.  d[0..511] = ln(Pw_test/Pw_ref) is in `dlog` (shared).
-// work: 2048 doubles of warp-private shared memory.
+// run by the two warps of the channel's test stream (t = thread within the stream, 0..63): the
+// 512- and 256-point transforms and the loops around them are shared; the last, 128-point
+// transform and the peak search are too small for that and stay on the first warp (which returns
+// the value).  `xch`: 6 doubles of shared memory for the cross-warp sums.  d[0..511] =
+// ln(Pw_test/Pw_ref) is in `dlog` (shared); work: the first 1536 doubles of the ref stream's buffer.
 //
 // Transform sizes are halved wherever a sequence is real:
 //   - both forward transforms of do_xcorr (movs.c:1300-1303) are packed into ONE
@@ -268,20 +278,20 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
 //   - the inverse of the Hermitian product (movs.c:1304-1313) is a 256-point complex
 //     FFT of the even/odd recombined spectrum;
 //   - the final 256-point real transform (movs.c:1428) is a 128-point complex FFT.
-__device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* dlog, double* work,
-                              const double2* __restrict__ tw, int lane) {
+__device__ double ehs_channel_pair(const DeviceTables* __restrict__ T, const double* dlog, double* work,
+                                   const double2* __restrict__ tw, int t, StreamSync sync, double* xch) {
+  const int lane = t & 31, half = t >> 5;
   double2* za = reinterpret_cast<double2*>(work);         // 512 complex
   double2* zb = reinterpret_cast<double2*>(work) + 512;   // 256 complex (+ 129 doubles of |C|^2)
-  const int sl9 = fft_slot_rt<9>(lane);
-  const int sl8 = fft_slot_rt<8>(lane);
+  const int sl9 = fft_slot_rt<9>(t);
+  const int sl8 = fft_slot_rt<8>(t);
 #pragma unroll
-  for (int u = 0; u < 16; u++) {
-    const double v = dlog[lane + 32 * u];
-    za[sl9 ^ fft_slot<9>(32 * u)] = make_double2(v, u < 8 ? v : 0.);
+  for (int u = 0; u < 8; u++) {
+    const double v = dlog[t + 64 * u];
+    za[sl9 ^ fft_slot<9>(64 * u)] = make_double2(v, u < 4 ? v : 0.);
   }
-  __syncwarp();
-  warp_fft<9>(za, tw, lane);
-  // G[q] = F1[q] conj(F2[q]) / 512 with F1 = (Z[q] + conj Z[-q]) / 2, F2 = (Z[q] - conj Z[-q]) / 2i
+  sync();
+  group_fft<9, 64, StreamSync>(za, tw, t, sync);
   auto g_of = [&](int q) {
     const double2 p = za[fft_swz(q & 511)];
     const double2 m = za[fft_swz((512 - q) & 511)];
@@ -289,37 +299,32 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
     const double f2r = 0.5 * (p.y + m.y), f2i = -0.5 * (p.x - m.x);
     return make_double2((f1r * f2r + f1i * f2i) / (2 * kMaxLag), (f2r * f1i - f1r * f2i) / (2 * kMaxLag));
   };
-  // real inverse of length 512 through a 256-point complex transform: with
-  // E = G[k] + conj G[256-k], O = (G[k] - conj G[256-k]) e^{+2 pi i k / 512}, Z' = E + i O,
-  // c[2m] + i c[2m+1] = sum_k Z'[k] e^{+2 pi i k m / 256} = conj FFT(conj Z')[m]
 #pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const int k = lane + 32 * u;
+  for (int u = 0; u < 4; u++) {
+    const int k = t + 64 * u;
     const double2 a = g_of(k), b = g_of(256 - k);
     const double er = a.x + b.x, ei = a.y - b.y;
     const double dr = a.x - b.x, di = a.y + b.y;
     const double2 w = tw[2 * k];                      // e^{-2 pi i k / 512}; its conjugate is needed
     const double orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
-    zb[sl8 ^ fft_slot<8>(32 * u)] = make_double2(er - oi, -(ei + orr));   // conj(E + i O)
+    zb[sl8 ^ fft_slot<8>(64 * u)] = make_double2(er - oi, -(ei + orr));   // conj(E + i O)
   }
-  __syncwarp();
-  warp_fft<8>(zb, tw, lane);
-  // lane owns lags i = 8*lane .. 8*lane+7: c[2m] = Re, c[2m+1] = -Im of element m = 4*lane + p
-  double c[8];
+  sync();
+  group_fft<8, 64, StreamSync>(zb, tw, t, sync);
+  // thread owns lags i = 4 t .. 4 t + 3: c[2m] = Re, c[2m+1] = -Im of element m = 2 t + p
+  double c[4];
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const double2 v = zb[fft_swz(4 * lane + p)];
+  for (int p = 0; p < 2; p++) {
+    const double2 v = zb[fft_swz(2 * t + p)];
     c[2 * p] = v.x;
     c[2 * p + 1] = -v.y;
   }
-  // normalisation by the running window energy (movs.c:1405-1418):
-  //   c[i] /= sqrt(d0 * dk_i),  dk_i = d0 + sum_{j<i} (d[j+256]^2 - d[j]^2)
-  const double d0 = __shfl_sync(0xffffffffu, c[0], 0);
-  double term[8];
+  // c[i] /= sqrt(d0 * dk_i), dk_i = d0 + sum_{j<i} (d[j+256]^2 - d[j]^2)   (movs.c:1405-1418)
+  double term[4];
   double local = 0.;
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
-    const int i = 8 * lane + e;
+  for (int e = 0; e < 4; e++) {
+    const int i = 4 * t + e;
     const double hi = dlog[i + kMaxLag], lo = dlog[i];
     term[e] = hi * hi - lo * lo;
     local += term[e];
@@ -330,28 +335,32 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
     const double x = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += x;
   }
-  double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) excl = 0.;
-  double dk = d0 + excl;
+  if (t == 0) xch[0] = c[0];
+  if (t == 31) xch[1] = incl;   // total of the first warp
+  sync();
+  const double d0 = xch[0];
+  double dk = d0 + ((incl - local) + (half ? xch[1] : 0.));
   double csum = 0.;
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
+  for (int e = 0; e < 4; e++) {
     c[e] = c[e] * rsqrt(d0 * dk);   // c / sqrt(d0 dk) (movs.c:1415); same zero / NaN classes
     csum += c[e];
     dk += term[e];
   }
-  const double cavg = warp_sum(csum) / kMaxLag;
-  __syncwarp();
+  csum = warp_sum(csum);
+  if (lane == 0) xch[2 + half] = csum;
+  sync();
+  const double cavg = (xch[2] + xch[3]) / kMaxLag;
   // subtract mean, window (movs.c:1419-1421); 256 real points as 128 complex ones
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const int i = 8 * lane + 2 * p;
-    za[fft_slot_rt<7>(4 * lane + p)] =
+  for (int p = 0; p < 2; p++) {
+    const int i = 4 * t + 2 * p;
+    za[fft_slot_rt<7>(2 * t + p)] =
         make_double2((c[2 * p] - cavg) * T->ehs_window[i], (c[2 * p + 1] - cavg) * T->ehs_window[i + 1]);
   }
-  __syncwarp();
+  sync();
+  if (half) return 0.;
   warp_fft<7>(za, tw, lane);
-  // C[k] = E + e^{-2 pi i k / 256} O,  k = 0..128;  |C[k]|^2 into shared memory
   double* s2 = reinterpret_cast<double*>(zb);
   for (int k = lane; k <= kMaxLag / 2; k += 32) {
     const double2 p = za[fft_swz(k & 127)];
@@ -364,12 +373,10 @@ __device__ double ehs_channel(const DeviceTables* __restrict__ T, const double* 
     s2[k] = xr * xr + xi * xi;
   }
   __syncwarp();
-  // largest |C[k]|^2 among 1 <= k <= 128 that rises above its left neighbour
-  // (movs.c:1433-1440; NaNs never win a comparison, exactly as there)
   double best = 0.;
   for (int k = 1 + lane; k <= kMaxLag / 2; k += 32) {
-    const double s = s2[k], sp = s2[k - 1];
-    if (s > sp && s > best) best = s;
+    const double sv = s2[k], sp = s2[k - 1];
+    if (sv > sp && sv > best) best = sv;
   }
   return warp_max_nonan(best);
 }
@@ -392,15 +399,10 @@ struct FrameMail {
   float maxabs[kMaxChannels][2];
   int bw_ref_part[kMaxChannels][2];
   int bw_test_part[kMaxChannels][2];
+  double ehs_x[kMaxChannels][6];
   unsigned long long mbar;
 };
 
-// barrier of the two warps of one stream (ids 1..4), of the four warps of one channel
-// (ids 5, 6) and the arrive/wait pair that guards the ref buffer (ids 7, 8)
-struct StreamSync {
-  int id;
-  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-};
 __device__ __forceinline__ void chan_sync(int chan) {
   asm volatile("bar.sync %0, 128;" ::"r"(5 + chan) : "memory");
 }
@@ -418,8 +420,8 @@ __device__ __forceinline__ void refbuf_wait(int chan) {
 // that the four warps of a channel split into tasks:
 //   ref-h0 : grouping + spreading of the ref stream
 //   ref-h1 : grouping + spreading of the test stream
-//   test-h0: half of the ln spectrum ratio and of the noise bands, then the EHS
-//   test-h1: the other halves
+//   test-h0: half of the ln spectrum ratio and of the noise bands
+//   test-h1: the other halves; then both run the EHS together
 __global__ void __launch_bounds__(256, 3)
 fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned first_frame,
                   unsigned n_chunk_frames, double* __restrict__ records, RecordLayout L, int B,
@@ -704,14 +706,11 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     for (int i = 32 * hh + lane; i < B; i += 64)
       rec[L.off_noise + chan * B + i] = group_band_noise(T, spec_ref, spec_test, i);
     __threadfence_block();
-    if (role == 3) {
-      refbuf_arrive(chan);
-    } else {
-      refbuf_wait(chan);   // ln ratio complete, ref spectrum dead: its buffer carries the EHS transforms
-      double ehs = 0.;
-      if (ehs_valid) ehs = ehs_channel(T, dlog, buf_ref, tw, lane);
-      if (lane == 0) rec[L.off_ehs + chan] = ehs;
-    }
+    // both warps: ln ratio complete, ref spectrum dead -- its buffer carries the EHS transforms
+    refbuf_wait(chan);
+    double ehs = 0.;
+    if (ehs_valid) ehs = ehs_channel_pair(T, dlog, buf_ref, tw, t, StreamSync{1 + stream}, mail->ehs_x[chan]);
+    if (role == 2 && lane == 0) rec[L.off_ehs + chan] = ehs;
   }
 
   if (threadIdx.x == 0) {
