@@ -158,8 +158,8 @@ __device__ __forceinline__ double group_band_noise(const DeviceTables* __restric
 __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* sa, double* se,
                              double* se2, double* __restrict__ out, int lane) {
   const double dz02 = 0.2 * T->dz;
-  // four bands per lane, two at a time (instruction-level parallelism against code size)
-#pragma unroll 2
+  // four bands per lane, interleaved for instruction-level parallelism
+#pragma unroll
   for (int m = 0; m < 4; m++) {
     const int i = lane + 32 * m;
     const int ii = i < B ? i : B - 1;
@@ -697,7 +697,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   } else {
     // ---- ln spectrum ratio (movs.c:1396-1403) and noise in bands (movs.c:988-1000), in halves --
     const int hh = role - 2;
-#pragma unroll 2
+#pragma unroll 4
     for (int u = 0; u < 8; u++) {
       const int i = 256 * hh + lane + 32 * u;
       const double fref = spec_ref[i], ftest = spec_test[i];
