@@ -623,8 +623,10 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
       }
       const int per = std::min(per_max, e->advanced ? 1024 : 296);
       while (left > 0) {
-        sizes.push_back(std::min(per, left));
-        left -= sizes.back();
+        // basic mode: the very last sub-batches small, the job ends with their kernels
+        const int n = (!e->advanced && left <= per) ? std::min(left, 128) : std::min(per, left);
+        sizes.push_back(n);
+        left -= n;
       }
     }
     PairResult* d_all = nullptr;
