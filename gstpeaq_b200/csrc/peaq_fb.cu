@@ -30,6 +30,8 @@
 // reads the NEWEST sample (fb_buf[offset + 1456] == fb_buf[offset]).
 #include "peaq_engine.h"
 
+#include <cstdlib>
+
 namespace peaq {
 namespace {
 
@@ -180,6 +182,145 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   double2* dst = reinterpret_cast<double2*>(st + 6);
   const double2* src = reinterpret_cast<const double2*>(out + chunk_samples);
   for (int i = 0; i < kFbHist / 2; i++) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------
+// FB1p: the same filter as a TIME-PARALLEL block scan -- opt-in (PEAQ_B200_HP_PARALLEL=1), for
+// few, long items, where the exact recurrence above keeps a handful of threads busy for
+// 52 ns per sample.  The chunk is cut into blocks of kHpL samples:
+//   pass 0   every block from a zero recursive state (its input history x[n-1], x[n-2] is PCM,
+//            not state) -> zero-state end state e0[j]
+//   scan 0   per stream: s0[j+1] = e0[j] + M s0[j], M = homogeneous transition over kHpL samples
+//   pass 1   every block from s0[j] -> end state e1[j]
+//   scan 1   d[j+1] = (e1[j] - s0[j+1]) + M d[j];  s[j+1] = s0[j+1] + d[j+1]
+//   pass 2   every block from s[j] with the reference's own recurrence -> output
+// The near-double pole of the sections makes M s cancel ~30:1, so s0 alone is ~1e-10 off; the
+// refinement solves for the (tiny) correction d, whose own cancellation no longer matters.  What
+// remains is a different rounding sequence from the purely sequential run: ~1e-11 of the signal
+// level, i.e. up to ~1e-8 in bands 60 dB below it -- inside the 1e-6 bar of the MOVs, but not
+// the 1e-12 the default path keeps, hence opt-in.
+constexpr int kHpL = 512;
+
+struct HpTransition {
+  double m[4][4];   // [to][from] over (y1a, y2a, y1b, y2b)
+};
+
+template <int C, int MODE>
+__global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams, int n_blocks,
+                                       unsigned long long t0, unsigned chunk_samples,
+                                       double* __restrict__ hp, size_t hp_stride,
+                                       double* __restrict__ hp_state, const double* __restrict__ starts,
+                                       double* __restrict__ ends, int first_chunk) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_streams * n_blocks) return;
+  const int stream = (int)(idx / n_blocks), blk = (int)(idx - (long long)stream * n_blocks);
+  const int pair = stream / (2 * C), c = (stream >> 1) % C, side = stream & 1;
+  const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
+  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
+  const double lf = T->level_factor_fb;
+  const unsigned b0 = (unsigned)blk * kHpL;
+  const unsigned len = min((unsigned)kHpL, chunk_samples - b0);
+  double* st = hp_state + (size_t)stream * kHpStateDoubles;
+  Biquads f = Biquads{0, 0, 0, 0, 0, 0};
+  if (blk == 0) {
+    if (!first_chunk) {
+      f.x1 = st[0];
+      f.x2 = st[1];
+      if (MODE != 0) { f.y1a = st[2]; f.y2a = st[3]; f.y1b = st[4]; f.y2b = st[5]; }
+    }
+  } else {
+    const unsigned long long s1 = t0 + b0 - 1, s2 = t0 + b0 - 2;
+    f.x1 = (s1 < n ? __ldg(sig + s1 * C + c) : 0.f) * lf;
+    f.x2 = (s2 < n ? __ldg(sig + s2 * C + c) : 0.f) * lf;
+    if (MODE != 0) {
+      const double* bs = starts + ((size_t)stream * n_blocks + blk) * 4;
+      f.y1a = bs[0]; f.y2a = bs[1]; f.y1b = bs[2]; f.y2b = bs[3];
+    }
+  }
+  double* out = hp + (size_t)stream * hp_stride + kFbHist + b0;
+  for (unsigned i0 = 0; i0 < len; i0 += kHpBlock) {
+    double y[kHpBlock];
+#pragma unroll
+    for (int k = 0; k < kHpBlock; k++) {
+      const unsigned long long s = t0 + b0 + i0 + k;
+      const float x = (i0 + k < len && s < n) ? __ldg(sig + s * C + c) : 0.f;
+      y[k] = f.step(x * lf);   // fbearmodel.c:289
+    }
+    if (MODE == 2) {
+      if (i0 + kHpBlock <= len) {
+        double2* o = reinterpret_cast<double2*>(out + i0);
+#pragma unroll
+        for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[2 * k], y[2 * k + 1]);
+      } else {
+        for (int k = 0; k < kHpBlock && i0 + k < len; k++) out[i0 + k] = y[k];
+      }
+    }
+  }
+  if (MODE != 2) {
+    // (only full blocks feed the scans; the states past a partial last block are never used --
+    // but its recurrence ran kHpBlock-padded with zeros, so do not publish it)
+    double* be = ends + ((size_t)stream * n_blocks + blk) * 4;
+    be[0] = f.y1a; be[1] = f.y2a; be[2] = f.y1b; be[3] = f.y2b;
+  } else if (blk == n_blocks - 1) {
+    st[0] = f.x1; st[1] = f.x2; st[2] = f.y1a; st[3] = f.y2a; st[4] = f.y1b; st[5] = f.y2b;
+  }
+}
+
+// MODE 0: zero-state end states (in `a`) -> approximate start states, in place.
+// MODE 1: refinement; `a` holds the approximate starts, `b` the end states reached from them.
+template <int MODE>
+__global__ void fb_hp_par_scan_kernel(int n_streams, int n_blocks, const double* __restrict__ hp_state,
+                                      double* __restrict__ a, const double* __restrict__ b, HpTransition M,
+                                      int first_chunk) {
+  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stream >= n_streams) return;
+  double* pa = a + (size_t)stream * n_blocks * 4;
+  auto apply = [&](const double (&s)[4], const double (&e)[4], double (&o)[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      o[r] = fma(M.m[r][0], s[0], fma(M.m[r][1], s[1], fma(M.m[r][2], s[2], fma(M.m[r][3], s[3], e[r]))));
+  };
+  if (MODE == 0) {
+    const double* st = hp_state + (size_t)stream * kHpStateDoubles;
+    double s[4] = {0., 0., 0., 0.};
+    if (!first_chunk) { s[0] = st[2]; s[1] = st[3]; s[2] = st[4]; s[3] = st[5]; }
+    for (int j = 0; j < n_blocks; j++) {
+      const double e[4] = {pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]};
+      pa[4 * j] = s[0]; pa[4 * j + 1] = s[1]; pa[4 * j + 2] = s[2]; pa[4 * j + 3] = s[3];
+      double o[4];
+      apply(s, e, o);
+      s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+    }
+  } else {
+    const double* pb = b + (size_t)stream * n_blocks * 4;
+    double d[4] = {0., 0., 0., 0.};   // block 0 starts from the exact carried state
+    for (int j = 0; j + 1 < n_blocks; j++) {
+      double r[4], o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) r[k] = pb[4 * j + k] - pa[4 * (j + 1) + k];   // nearly equal: exact
+      apply(d, r, o);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        d[k] = o[k];
+        pa[4 * (j + 1) + k] += d[k];
+      }
+    }
+  }
+}
+
+__global__ void fb_hp_par_hist_kernel(double* __restrict__ hp, size_t hp_stride, double* __restrict__ hp_state,
+                                      unsigned chunk_samples, int mode, int first_chunk) {
+  const int stream = blockIdx.x;
+  double2* buf = reinterpret_cast<double2*>(hp + (size_t)stream * hp_stride);
+  double2* st = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + 6);
+  if (mode == 0) {
+    for (int i = threadIdx.x; i < kFbHist / 2; i += blockDim.x) buf[i] = first_chunk ? make_double2(0., 0.) : st[i];
+  } else {
+    // [history | chunk] is contiguous: the last kFbHist filtered samples, also for short chunks
+    const double* src = hp + (size_t)stream * hp_stride + chunk_samples;
+    double* dst = hp_state + (size_t)stream * kHpStateDoubles + 6;
+    for (int i = threadIdx.x; i < kFbHist; i += blockDim.x) dst[i] = src[i];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -526,6 +667,52 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
                          cudaStream_t stream) {
   const int n_streams = n_pairs * 2 * pcm.channels;
   if (n_streams <= 0) return cudaSuccess;
+  static const bool parallel = std::getenv("PEAQ_B200_HP_PARALLEL") && std::atoi(std::getenv("PEAQ_B200_HP_PARALLEL"));
+  if (parallel && chunk_samples >= 4 * kHpL) {
+    // time-parallel block scan (see FB1p above); scratch from the stream-ordered allocator
+    static const HpTransition M = [] {
+      HpTransition t;
+      for (int from = 0; from < 4; from++) {
+        double v[4] = {0., 0., 0., 0.};
+        v[from] = 1.;
+        for (int i = 0; i < kHpL; i++) {
+          const double h1 = 1.99517 * v[0] - 0.995174 * v[1];
+          const double h2 = h1 - 2. * v[0] + v[1] + 1.99799 * v[2] - 0.997998 * v[3];
+          v[1] = v[0]; v[0] = h1; v[3] = v[2]; v[2] = h2;
+        }
+        for (int to = 0; to < 4; to++) t.m[to][from] = v[to];
+      }
+      return t;
+    }();
+    const int n_blocks = (int)((chunk_samples + kHpL - 1) / kHpL);
+    const size_t n_state = (size_t)n_streams * n_blocks * 4;
+    double *sa = nullptr, *sb = nullptr;
+    cudaError_t e = cudaMallocAsync(&sa, n_state * sizeof(double), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocAsync(&sb, n_state * sizeof(double), stream);
+    if (e != cudaSuccess) return e;
+    const int fc = first_chunk ? 1 : 0;
+    const long long n_threads = (long long)n_streams * n_blocks;
+    const unsigned grid = (unsigned)((n_threads + 63) / 64), sgrid = (unsigned)((n_streams + 63) / 64);
+    fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 0, fc);
+    if (pcm.channels == 2) {
+      fb_hp_par_block_kernel<2, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
+      fb_hp_par_scan_kernel<0><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<2, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+      fb_hp_par_scan_kernel<1><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<2, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+    } else {
+      fb_hp_par_block_kernel<1, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
+      fb_hp_par_scan_kernel<0><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<1, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+      fb_hp_par_scan_kernel<1><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<1, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+    }
+    fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 1, fc);
+    cudaFreeAsync(sa, stream);
+    cudaFreeAsync(sb, stream);
+    return cudaGetLastError();
+  }
   // few threads per block so the streams spread over all SMs (latency-bound scan)
   const int block = 32;
   const int grid = (n_streams + block - 1) / block;

@@ -475,3 +475,37 @@ def test_unaligned_mono_batch_matches_oracle(advanced):
     for p, n in enumerate(lengths):
         want = H.oracle_run_pair(ref[p, :n], test[p, :n], ch, advanced=advanced)
         check_result(out[p], want, "mono pair %d len %d adv %d" % (p, n, advanced))
+
+
+def test_time_parallel_dc_reject_scan_option():
+    """PEAQ_B200_HP_PARALLEL=1 (block scan with refinement, for few long items) against the
+    default exact recurrence: excitations to 5e-9, MOVs / ODG to 1e-9 (measured 4e-10 / 3e-12)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import json, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import gstpeaq_b200 as G
+from signals import synth_pair
+ch = 2
+ref, test = synth_pair(77, 96000, ch)
+e = G.Engine(0, advanced=True)
+e.keep_records(True)
+out = e.run_host(ref, test, ch)
+exc, movs = e.fb_debug(1, ch)
+print(json.dumps({"movs": out["movs"][0][:5].tolist(), "odg": float(out["odg"][0]),
+                  "exc": np.asarray(exc[0]).ravel().tolist()}))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for par in ("0", "1"):
+        env = dict(os.environ, PEAQ_B200_HP_PARALLEL=par)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[par] = json.loads(p.stdout.strip().splitlines()[-1])
+    a, b = res["0"], res["1"]
+    assert a["exc"] != b["exc"]          # the option really took the other path
+    np.testing.assert_allclose(a["exc"], b["exc"], rtol=5e-9)
+    np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9, atol=1e-12)
+    assert abs(a["odg"] - b["odg"]) < 1e-9
