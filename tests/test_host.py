@@ -115,3 +115,32 @@ def test_filter_bank_recursion_tables_reproduce_the_taps():
             step = ph[1:, f] / ph[:-1, f]
             np.testing.assert_allclose(step ** 32, rp[f, 0], rtol=0, atol=1e-12)
         assert t["D"] == 1 + (1456 - N) // 2
+
+
+def test_filter_bank_recursion_equals_direct_fir_in_numpy():
+    """the algorithm of fb_bank_rec_kernel replayed in numpy from the library's own tables: the
+    three one-step recursions reproduce the direct FIR (taps of fbearmodel.c:213-220 at delays
+    D + n, fbearmodel.c:408) on a random signal"""
+    import gstpeaq_b200 as G
+    rng = np.random.default_rng(5)
+    n_sub = 120
+    x = rng.standard_normal(32 * n_sub + 1) * 1e3
+
+    def at(i):   # x[i], zero before the start of the signal
+        i = np.asarray(i)
+        return np.where(i >= 0, x[np.clip(i, 0, None)], 0.0)
+
+    for band in (1, 7, 19, 30, 39):   # (band 0 additionally carries the reference's ring-buffer alias)
+        t = G.fb_filter_tables(band)
+        N, D, ph, rp = t["N"], t["D"], t["ph"], t["rpow"]
+        h = np.concatenate([t["h"], np.conj(t["h"][-2::-1])])   # taps 0..N, h[0] = h[N] = 0
+        n = np.arange(1, N)
+        k = np.arange(32)
+        S = np.zeros(3, complex)
+        worst, scale = 0.0, 0.0
+        for s in range(n_sub):
+            direct = np.sum(h[n] * at(32 * s - D - n))
+            S = rp[:, 0] * S + ph[:, :3].T @ at(32 * s - D - k) + ph[:, 3:].T @ at(32 * s - D - k - N)
+            worst = max(worst, abs(S.sum() - direct))
+            scale = max(scale, abs(direct))
+        assert worst < 1e-12 * scale, (band, worst, scale)
