@@ -5,19 +5,28 @@
   python bench.py --impl reference [...]                        (reference CPU arm)
   torchrun ... bench.py --gpus N ...                            (N > 1, one rank per GPU)
 
-Workload (BASELINE.json configs[1]): batch = 4096 pairs per GPU of 10 s, 48 kHz,
-stereo, basic mode; pairs are independent, so N GPUs process N*4096 pairs (weak
-scaling) and the only collective is the gather of the per-pair results.
-A step = one pass of the hot path over the whole batch.  One PEAQ frame = one
-1024-sample step of one pair (468 per 10 s pair incl. the padded last frame).
+Headline workload (BASELINE.json configs[1]; configs[3] when N = 8): 4096 pairs
+per GPU (8192 per GPU at N = 8, i.e. 65536 global) of 10 s, 48 kHz, stereo,
+basic mode.  Pairs are independent, so N GPUs process N x that many pairs (weak
+scaling); the only collective is the gather of the per-pair results, which is
+INSIDE every timed step.  A step = one pass of the hot path over the whole
+batch.  One PEAQ frame = one 1024-sample step of one pair (468 per 10 s pair
+incl. the padded last frame).
 
-The JSON line carries `value` (device-resident inputs), `e2e` (host buffers
-through the C-ABI batch call, H2D/D2H inside the timed region), `roofline`
-(frame kernel vs the measured HBM copy bandwidth; algorithmic bytes = 16384 B
-read per frame) and `cpu_baseline` (the reference's own C code on
-the host cores, bounded sample).
+The ONE JSON line carries
+  value / ms_per_step  device-resident inputs, CUDA events on the engine's stream + the gather
+  e2e                  pinned HOST buffers through the C-ABI batch call, H2D/D2H in the timed region
+  roofline             dominant kernel vs the measured HBM copy bandwidth (16384 algorithmic
+                       bytes per frame) and vs the measured FP64 peak
+  cpu_baseline         the reference's own C code on the host cores, bounded sample (N = 1)
+  parity               GPU results vs the reference's results for the same first pairs
+                       (the second half of BASELINE.json's metric: "ODG delta vs reference")
+  modes.advanced       the same set of fields for BASELINE configs[2]
+  long_items           32 pairs per GPU of --long-seconds (BASELINE configs[4] shape), both modes
+The run FAILS (exit 3, line still printed) if any |dODG| or |dDI| vs the reference exceeds 1e-4.
 """
 import argparse
+import hashlib
 import json
 import multiprocessing as mp
 import os
@@ -29,20 +38,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PAIR_SECONDS = 10
-N_SAMPLES = 48000 * PAIR_SECONDS
 CHANNELS = 2
+PAIR_SECONDS = 10
 PAIRS_PER_GPU = 4096
-BYTES_PER_FRAME = 1024 * CHANNELS * 4 * 2        # algorithmic HBM read per PEAQ frame
-# CPU arm: pairs per host core and step (basic: ~3 s of work per core, advanced ~20 s)
-CPU_PAIRS_PER_CORE = 12
+PAIRS_PER_GPU_8 = 8192                            # BASELINE configs[3]: 65536 pairs over 8 GPUs
+LONG_PAIRS_PER_GPU = 32                           # BASELINE configs[4]: 256 pairs over 8 GPUs
+BYTES_PER_FRAME = 1024 * CHANNELS * 4 * 2         # algorithmic HBM read per PEAQ frame
 METRIC = "48 kHz stereo PEAQ frames/sec"
 UNIT = "frames/s"
+ODG_LIMIT = 1e-4                                  # SURVEY 8d parity gate
+# CPU sample sizes (pairs per host core): about 3 s (basic) / 3 s (advanced) of work per core
+CPU_PAIRS_PER_CORE = {"basic": 12, "advanced": 4}
+KERNEL_SOURCES = ["peaq_frames.cu", "peaq_fft.cuh", "peaq_scan.cu", "peaq_fused.cu", "peaq_fb.cu",
+                  "peaq_scan_adv.cu", "peaq_math.cuh", "peaq_engine.h"]
 
 
-def frames_per_pair():
+def frames_for(n_samples):
     import gstpeaq_b200 as G
-    return G.frames_for_samples(N_SAMPLES)
+    return G.frames_for_samples(n_samples)
 
 
 # --------------------------------------------------------------------------
@@ -51,52 +64,88 @@ def frames_per_pair():
 # smoke() that executes anything under oracle/.
 
 def _cpu_worker(args):
-    first, count, kind, mode = args
-    global MODE
-    MODE = mode
+    first, count, kind, mode, n_samples = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
     import gstpeaq_b200 as G
     import refharness as H
-    ref, test = G.synth_pairs_host(first, count, N_SAMPLES, CHANNELS)   # untimed input generation
+    ref, test = G.synth_pairs_host(first, count, n_samples, CHANNELS)   # untimed input generation
     t0 = time.perf_counter()
-    frames = 0
-    odgs = []
+    rows = []
     for p in range(count):
         if kind == "reference":
-            r = H.RefPeaq(MODE == "advanced", 92.0, CHANNELS).run(ref[p], test[p])
+            r = H.RefPeaq(mode == "advanced", 92.0, CHANNELS).run(ref[p], test[p])
         else:
-            r = H.oracle_run_pair(ref[p], test[p], CHANNELS, advanced=(MODE == "advanced"))
-        frames += r["frames_fft"]
-        odgs.append(r["odg"])
-    return frames, time.perf_counter() - t0, odgs
+            r = H.oracle_run_pair(ref[p], test[p], CHANNELS, advanced=(mode == "advanced"))
+        rows.append({"pair": first + p, "odg": float(r["odg"]), "di": float(r["di"]),
+                     "movs": [float(x) for x in r["movs"]], "frames_fft": int(r["frames_fft"]),
+                     "frames_fb": int(r["frames_fb"]),
+                     "loudness_reached_frame": int(r["loudness_reached_frame"])})
+    return time.perf_counter() - t0, rows
 
 
 def cpu_kind():
     return "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpeaq_ref.so")) else "port"
 
 
-def run_cpu_sample(n_pairs, cores):
-    """frames/s of the CPU path over `n_pairs` pairs spread over `cores` processes
-    (processes, not threads: the reference lazily initialises static FFT plans
-    and GTypes without locking)."""
+def run_cpu_sample(n_pairs, cores, mode, n_samples, first_pair=0):
+    """CPU path over pairs [first_pair, first_pair + n_pairs) spread over `cores` processes
+    (processes, not threads: the reference lazily initialises static FFT plans and GTypes
+    without locking).  Returns (frames/s, frames, busy s, wall s, kind, rows)."""
     kind = cpu_kind()
     per = max(1, n_pairs // cores)
     jobs = []
     first = 0
     while first < n_pairs:
         c = min(per, n_pairs - first)
-        jobs.append((first, c, kind, MODE))
+        jobs.append((first_pair + first, c, kind, mode, n_samples))
         first += c
     ctx = mp.get_context("spawn")
     with ctx.Pool(min(cores, len(jobs))) as pool:
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, jobs)
         wall = time.perf_counter() - t0
-    frames = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)
+    rows = [r for job in res for r in job[1]]
+    frames = sum(r["frames_fft"] for r in rows)
+    busy = max(job[0] for job in res)
     # throughput over the slowest worker's compute time (generation excluded)
-    return frames / busy, frames, busy, wall, kind
+    return frames / busy, frames, busy, wall, kind, rows
+
+
+def parity_block(gpu_rows, cpu_rows, kind, what):
+    """GPU results against the CPU path's for the same pairs: the reference's acceptance style
+    (src/checkconformanceresults.sh:17-39) -- number and comparison together."""
+    import numpy as np
+    d_odg = d_di = rel_mov = 0.0
+    ints_equal = True
+    nan_mismatch = 0
+    for c in cpu_rows:
+        g = gpu_rows[c["pair"]]
+        for key in ("odg", "di"):
+            a, b = float(g[key]), c[key]
+            if np.isnan(a) or np.isnan(b):
+                nan_mismatch += int(np.isnan(a) != np.isnan(b))
+                continue
+            d = abs(a - b)
+            if key == "odg":
+                d_odg = max(d_odg, d)
+            else:
+                d_di = max(d_di, d)
+        n = len(c["movs"])
+        for i in range(n):
+            a, b = float(g["movs"][i]), c["movs"][i]
+            if np.isnan(a) or np.isnan(b):
+                nan_mismatch += int(np.isnan(a) != np.isnan(b))
+                continue
+            rel_mov = max(rel_mov, abs(a - b) / max(abs(b), 1e-9))
+        ints_equal &= (int(g["frames_fft"]) == c["frames_fft"] and int(g["frames_fb"]) == c["frames_fb"] and
+                       int(g["loudness_reached_frame"]) == c["loudness_reached_frame"])
+    ok = bool(d_odg <= ODG_LIMIT and d_di <= ODG_LIMIT and ints_equal and nan_mismatch == 0)
+    return {"against": "oracle/_ref = the reference's C code compiled here" if kind == "reference"
+                       else "oracle/ = C restatement of the reference",
+            "pairs_compared": len(cpu_rows), "what": what,
+            "max_abs_delta_odg": d_odg, "max_abs_delta_di": d_di, "max_rel_delta_mov": rel_mov,
+            "integer_fields_equal": bool(ints_equal), "nan_mismatches": nan_mismatch,
+            "limit_abs_delta_odg": ODG_LIMIT, "ok": ok}
 
 
 def reference_arm(args):
@@ -104,22 +153,25 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_pairs = max(cores, min(PAIRS_PER_GPU, cores * CPU_PAIRS_PER_CORE))
+    mode = args.mode
+    pairs_gpu = pairs_per_gpu(args.gpus)
+    n_samples = 48000 * PAIR_SECONDS
+    n_pairs = max(cores, min(pairs_gpu, cores * CPU_PAIRS_PER_CORE[mode]))
     times = []
     frames = 0
     kind = cpu_kind()
     for i in range(args.warmup + args.steps):
-        fps, frames, busy, wall, kind = run_cpu_sample(n_pairs, cores)
+        fps, frames, busy, wall, kind, _ = run_cpu_sample(n_pairs, cores, mode, n_samples)
         if i >= args.warmup:
             times.append(busy)
     ms = 1e3 * sum(times) / max(len(times), 1)
     value = frames / (ms / 1e3)
-    sample = "%d of %d pairs x %d s per step on %d processes" % (n_pairs, PAIRS_PER_GPU, PAIR_SECONDS, cores)
+    sample = "%d of %d pairs x %d s per step on %d processes" % (n_pairs, pairs_gpu, PAIR_SECONDS, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, mode, pairs_gpu, PAIR_SECONDS),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -128,16 +180,22 @@ def reference_arm(args):
     return 0
 
 
-MODE = "basic"
+def pairs_per_gpu(n_gpus):
+    return PAIRS_PER_GPU_8 if n_gpus >= 8 else PAIRS_PER_GPU
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, mode, pairs_gpu, seconds):
+    if seconds == PAIR_SECONDS:
+        cfg = 2 if mode == "advanced" else (3 if n_gpus >= 8 else 1)
+    else:
+        cfg = 4
     return {"workload": "batch=%d synthetic 48 kHz stereo %d s pairs per GPU, %s mode (BASELINE configs[%d])"
-                        % (PAIRS_PER_GPU, PAIR_SECONDS, MODE, 1 if MODE == "basic" else 2),
-            "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus,
-            "frames_per_pair": 468, "channels": CHANNELS, "mode": MODE,
-            "parallelism": "pairs sharded over %d GPU(s), result gather only" % n_gpus,
-            "l2": "inputs (31.5 GB per GPU) far exceed the 126 MB L2; no explicit flush"}
+                        % (pairs_gpu, seconds, mode, cfg),
+            "pairs_per_gpu": pairs_gpu, "global_pairs": pairs_gpu * n_gpus,
+            "frames_per_pair": frames_for(48000 * seconds), "channels": CHANNELS, "mode": mode,
+            "parallelism": "pairs sharded over %d GPU(s); all_gather of the result rows inside every step" % n_gpus,
+            "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush"
+                  % (pairs_gpu * 48000 * seconds * CHANNELS * 4 * 2 / 1e9)}
 
 
 # --------------------------------------------------------------------------
@@ -203,114 +261,182 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_frame():
-    """dram bytes per PEAQ frame of the mode's dominant kernel from the committed ncu capture, or None"""
-    p = os.path.join(ROOT, "profiles", "ncu_frame_kernel.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["dram_bytes_per_frame" if MODE == "basic" else "bank_dram_bytes_per_frame"])
-        except Exception:
-            return None
-    return None
+def kernel_source_hash():
+    """sha256 over the kernel sources: ties profiles/ncu_kernels.json to the code it was captured from"""
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        p = os.path.join(ROOT, "gstpeaq_b200", "csrc", name)
+        if os.path.exists(p):
+            h.update(name.encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
 
 
-def our_arm(args):
-    import numpy as np
+def ncu_facts(kernel):
+    """Per-frame facts of `kernel` from the committed `ncu --set full` capture (profiles/ncu_kernels.json,
+    written by scripts/ncu_to_json.py), or ({}, reason) when absent or captured from other sources."""
+    p = os.path.join(ROOT, "profiles", "ncu_kernels.json")
+    if not os.path.exists(p):
+        return {}, "profiles/ncu_kernels.json absent"
+    try:
+        doc = json.load(open(p))
+    except Exception as exc:
+        return {}, "unreadable: %s" % exc
+    if doc.get("source_hash") != kernel_source_hash():
+        return {}, "stale: captured from sources %s, tree is %s" % (doc.get("source_hash"), kernel_source_hash())
+    k = doc.get("kernels", {}).get(kernel)
+    if not k:
+        return {}, "kernel not in the capture"
+    return k, None
+
+
+class Ctx:
+    pass
+
+
+def make_ctx(args):
     import gstpeaq_b200 as G
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    torch = None
-    if world > 1:
+    c = Ctx()
+    c.args = args
+    c.G = G
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    c.dist = None
+    c.torch = None
+    if c.world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if G.device_count() <= local_rank:
-        raise G.PeaqError("no CUDA device for rank %d: the engine has no CPU fallback" % rank)
+        torch.cuda.set_device(c.local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", c.local_rank))
+        c.dist = dist
+        c.torch = torch
+    if G.device_count() <= c.local_rank:
+        raise G.PeaqError("no CUDA device for rank %d: the engine has no CPU fallback" % c.rank)
+    c.L = G.load_library()
+    c.engines = {}
+    try:
+        c.fp64_peak = float(c.L.peaq_b200_fp64_peak_tflops(c.local_rank))
+    except Exception:
+        c.fp64_peak = -1.0
+    return c
 
-    from gstpeaq_b200 import parallel
-    n_global = PAIRS_PER_GPU * world
-    first, count = parallel.shard_range(n_global, rank, world)
-    fpp = frames_per_pair()
-    L = G.load_library()
-    eng = G.Engine(local_rank, advanced=(MODE == "advanced"))
-    stride = N_SAMPLES * CHANNELS
-    nbytes = count * stride * 4
-    dref = G.DeviceBuffer(local_rank, nbytes)
-    dtest = G.DeviceBuffer(local_rank, nbytes)
-    G._check(L.peaq_b200_synth_pairs(local_rank, dref.ptr, dtest.ptr, stride, count, first, N_SAMPLES, CHANNELS))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
+def engine_for(c, mode):
+    if mode not in c.engines:
+        c.engines[mode] = c.G.Engine(c.local_rank, advanced=(mode == "advanced"))
+    return c.engines[mode]
 
-    def step():
-        return eng.run_device(dref.ptr, dtest.ptr, count, stride, CHANNELS, N_SAMPLES)
 
-    for _ in range(args.warmup):
-        out = step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = eng.launch_count()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms = k1_ms = k2_ms = bank_ms = 0.0
-    for _ in range(args.steps):
-        out = step()
-        dev_ms += eng.last_ms(0)       # CUDA events on the engine's stream
-        k1_ms += eng.last_ms(1)
-        k2_ms += eng.last_ms(2)
-        bank_ms += eng.last_ms(5)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+def barrier(c):
+    if c.dist is not None:
+        c.dist.barrier()
+        c.torch.cuda.synchronize()
 
-    # gather of the per-pair results (the path's only collective), outside the
-    # timed steps: it moves 128 B per pair once per job
-    if dist is not None:
-        full = parallel.gather_results(out, n_global, torch.device("cuda", local_rank))
-        t = torch.tensor([dev_ms, wall_ms, k1_ms, k2_ms, bank_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, k1_ms, k2_ms, bank_ms = [float(x) for x in t.tolist()]
-    else:
-        full = out
-    frames_step = int(full["frames_fft"].sum())
-    assert frames_step == n_global * fpp, (frames_step, n_global * fpp)
-    nan_odg = int(np.isnan(full["odg"]).sum())
-    ms_per_step = dev_ms / args.steps
-    value = frames_step / (ms_per_step / 1e3)
 
-    # ---- end to end: host (pinned) buffers through the batch call ------------
-    e2e = None
-    # pin this rank to the CPUs next to its GPU while the host buffers are allocated and used:
-    # with the default first-touch policy they then live on the GPU's NUMA node, and 8 ranks do
-    # not pull 250 GB per step across the socket interconnect
-    old_affinity = None
+def allmax(c, values):
+    if c.dist is None:
+        return [float(v) for v in values]
+    t = c.torch.tensor(list(values), dtype=c.torch.float64, device="cuda")
+    c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def pin_to_gpu_cpus(c):
+    """pin this rank to the CPUs next to its GPU while the host buffers are allocated and used: with
+    the default first-touch policy they then live on the GPU's NUMA node"""
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        h = pynvml.nvmlDeviceGetHandleByIndex(c.local_rank)
         n_words = (os.cpu_count() + 63) // 64
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
         cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
         if cpus:
-            old_affinity = os.sched_getaffinity(0)
-            os.sched_setaffinity(0, cpus & old_affinity or old_affinity)
+            old = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus & old or old)
+            return old
     except Exception:
-        old_affinity = None
+        pass
+    return None
+
+
+def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, what):
+    """One workload (mode, pairs per GPU, item length) measured like the headline: resident steps
+    with the gather inside, the end-to-end call from pinned host memory, the dominant kernel's
+    roofline, the CPU sample and the parity of the GPU results against it."""
+    import numpy as np
+    G, L = c.G, c.L
+    from gstpeaq_b200 import parallel
+    n_samples = 48000 * seconds
+    fpp = frames_for(n_samples)
+    n_global = pairs_gpu * c.world
+    first, count = parallel.shard_range(n_global, c.rank, c.world)
+    eng = engine_for(c, mode)
+    stride = n_samples * CHANNELS
+    nbytes = count * stride * 4
+    dref = G.DeviceBuffer(c.local_rank, nbytes)
+    dtest = G.DeviceBuffer(c.local_rank, nbytes)
+    G._check(L.peaq_b200_synth_pairs(c.local_rank, dref.ptr, dtest.ptr, stride, count, first, n_samples, CHANNELS))
+    dev = c.torch.device("cuda", c.local_rank) if c.dist is not None else None
+
+    def step():
+        """one pass over this rank's pairs + the path's only collective; returns (rows, engine ms, gather ms)"""
+        out = eng.run_device(dref.ptr, dtest.ptr, count, stride, CHANNELS, n_samples)
+        ms = eng.last_ms(0)            # CUDA events on the engine's stream
+        gms = 0.0
+        full = out
+        if c.dist is not None:
+            e0 = c.torch.cuda.Event(enable_timing=True)
+            e1 = c.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            full = parallel.gather_results(out, n_global, dev)      # NCCL all_gather on torch's current stream
+            e1.record()
+            e1.synchronize()
+            gms = e0.elapsed_time(e1)
+        return out, full, ms, gms
+
+    for _ in range(warmup):
+        out, full, _, _ = step()
+    sampler = ClockSampler(c.local_rank)
+    if c.rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    barrier(c)
+    t0 = time.perf_counter()
+    dev_ms = gather_ms = 0.0
+    kms = [0.0] * 7
+    for _ in range(steps):
+        out, full, ms, gms = step()
+        dev_ms += ms
+        gather_ms += gms
+        for i in range(1, 7):
+            kms[i] += eng.last_ms(i)
+    barrier(c)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if c.rank == 0 else None
+    red = allmax(c, [dev_ms + gather_ms, wall_ms, gather_ms] + kms)
+    step_ms, wall_ms, gather_ms = red[0] / steps, red[1] / steps, red[2] / steps
+    kms = [x / steps for x in red[3:]]
+    frames_step = int(full["frames_fft"].sum())
+    assert frames_step == n_global * fpp, (frames_step, n_global * fpp)
+    value = frames_step / (step_ms / 1e3)
+    res = {"value": value, "unit": UNIT, "ms_per_step": step_ms, "wall_ms_per_step": wall_ms,
+           "gather_ms_per_step": gather_ms, "steps": steps, "warmup": warmup,
+           "config": workload_config(c.world, mode, pairs_gpu, seconds), "clocks": clocks,
+           "gpu_launches": int(launches), "nan_odg_pairs": int(np.isnan(full["odg"]).sum()),
+           "odg_min": float(np.nanmin(full["odg"])), "odg_max": float(np.nanmax(full["odg"]))}
+
+    # ---- end to end: pinned HOST buffers through the batch call --------------------
+    old_affinity = pin_to_gpu_cpus(c)
     try:
         e2e_pairs = count
         try:
             import psutil
             # every rank of the node pins its own buffers at the same time
-            avail = psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
-            while e2e_pairs > 64 and 2 * e2e_pairs * stride * 4 * 1.3 > avail:
+            avail = psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", c.world)))
+            while e2e_pairs > 8 and 2 * e2e_pairs * stride * 4 * 1.3 > avail:
                 e2e_pairs //= 2
         except Exception:
             pass
@@ -319,95 +445,166 @@ def our_arm(args):
         pt = G.C.c_void_p()
         G._check(L.peaq_b200_host_alloc_pinned(hb, G.C.byref(pr)))
         G._check(L.peaq_b200_host_alloc_pinned(hb, G.C.byref(pt)))
-        G._check(L.peaq_b200_memcpy_d2h(local_rank, pr.value, dref.ptr, hb))
-        G._check(L.peaq_b200_memcpy_d2h(local_rank, pt.value, dtest.ptr, hb))
+        G._check(L.peaq_b200_memcpy_d2h(c.local_rank, pr.value, dref.ptr, hb))
+        G._check(L.peaq_b200_memcpy_d2h(c.local_rank, pt.value, dtest.ptr, hb))
         dref.free()
         dtest.free()
-        e2e_steps = max(1, min(args.steps, 3))
-        eng._run(pr.value, pt.value, e2e_pairs, stride, CHANNELS, None, N_SAMPLES, on_device=False)  # warm-up
-        barrier()
+        eng._run(pr.value, pt.value, e2e_pairs, stride, CHANNELS, None, n_samples, on_device=False)  # warm-up
+        barrier(c)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            o2 = eng._run(pr.value, pt.value, e2e_pairs, stride, CHANNELS, None, N_SAMPLES, on_device=False)
-        barrier()
+            o2 = eng._run(pr.value, pt.value, e2e_pairs, stride, CHANNELS, None, n_samples, on_device=False)
+            if c.dist is not None:
+                parallel.gather_results(o2, e2e_pairs * c.world, dev)
+        barrier(c)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        if dist is not None:
-            t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        e2e = {"value": e2e_pairs * world * fpp / (e2e_ms / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": 2 * hb * world, "d2h_bytes_per_step": e2e_pairs * world * 128,
-               "ms_per_step": e2e_ms, "pairs_per_gpu": e2e_pairs, "steps": e2e_steps,
-               "host_memory": "pinned", "odg_equal_to_resident_run": bool(np.array_equal(o2["odg"], out["odg"][:e2e_pairs], equal_nan=True))}
+        e2e_ms = allmax(c, [e2e_ms])[0]
+        res["e2e"] = {"value": e2e_pairs * c.world * fpp / (e2e_ms / 1e3), "unit": UNIT,
+                      "h2d_bytes_per_step": 2 * hb * c.world, "d2h_bytes_per_step": e2e_pairs * c.world * 128,
+                      "ms_per_step": e2e_ms, "pairs_per_gpu": e2e_pairs, "steps": e2e_steps,
+                      "host_memory": "pinned",
+                      "bit_equal_to_resident_run": bool(np.array_equal(o2["odg"], out["odg"][:e2e_pairs], equal_nan=True))}
         L.peaq_b200_host_free_pinned(pr.value)
         L.peaq_b200_host_free_pinned(pt.value)
     except Exception as exc:   # report, never hide
-        e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+        res["e2e"] = {"value": None, "unit": UNIT, "error": str(exc)}
+        dref.free()
+        dtest.free()
     if old_affinity is not None:
         os.sched_setaffinity(0, old_affinity)   # the CPU baseline below uses every core
 
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
+    if c.rank != 0:
+        barrier(c)
+        return res, out
 
+    # ---- roofline of the dominant kernel -------------------------------------------
+    # Algorithmic bytes per launch set = 16384 B x the frames one rank's launches cover (SURVEY 8d:
+    # both modes read the PCM once per ear model); duration = CUDA-event time of those launches
+    # inside the timed steps.
     peak, peak_src = measured_peak_gbs()
-    # dominant kernel: fft_frames_kernel (basic) / fb_bank_rec_kernel (advanced).  Algorithmic
-    # bytes per launch = 16384 B x the frames the launch covers (both modes read the
-    # PCM once per ear model); duration = CUDA-event time of those launches inside the timed
-    # steps (per GPU: the frames of one rank)
     frames_rank = count * fpp
-    dom_ms = (k1_ms if MODE == "basic" else bank_ms) / args.steps
-    achieved = frames_rank * BYTES_PER_FRAME / (dom_ms / 1e3) / 1e9
-    traffic = ncu_traffic_per_frame()
-    roofline = {"bound": "hbm", "kernel": "fft_frames_kernel" if MODE == "basic" else "fb_bank_rec_kernel",
-                "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": traffic * frames_rank if traffic else None,
+    if mode == "basic":
+        fused = kms[1] > 0 and kms[2] == 0
+        kernel = "peaq_fused_basic_kernel" if fused else "fft_frames_kernel"
+        dom_ms = kms[1]
+    else:
+        kernel = "fb_bank_rec_kernel"
+        dom_ms = kms[5]
+    roofline = {"bound": "hbm", "kernel": kernel, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_set": frames_rank * BYTES_PER_FRAME,
-                "kernel_ms_per_step": dom_ms, "frame_kernel_ms_per_step": k1_ms / args.steps,
-                "scan_kernel_ms_per_step": k2_ms / args.steps,
-                "kernel_share_of_step": dom_ms * args.steps / dev_ms,
-                "note": "FP64 latency/issue bound in practice (DESIGN.md 3); HBM fraction reported as the north star asks"}
+                "kernel_ms_per_step": dom_ms, "frame_kernel_ms_per_step": kms[1],
+                "scan_kernel_ms_per_step": kms[2], "fb_kernels_ms_per_step": kms[4],
+                "note": "FP64 issue/latency bound in practice (DESIGN.md 3); the HBM fraction is what the north star asks for"}
+    if dom_ms > 0:
+        roofline["achieved"] = frames_rank * BYTES_PER_FRAME / (dom_ms / 1e3) / 1e9
+        roofline["frac"] = roofline["achieved"] / peak
+        roofline["kernel_share_of_step"] = dom_ms / (step_ms - gather_ms)
+    facts, why = ncu_facts(kernel)
+    if facts:
+        roofline["traffic"] = facts["dram_bytes_per_frame"] * frames_rank
+        roofline["traffic_per_frame"] = facts["dram_bytes_per_frame"]
+        roofline["ncu_capture"] = facts.get("capture")
+        roofline["fp64_pipe_active_pct_ncu"] = facts.get("fp64_pipe_active_pct")
+        roofline["issue_active_pct_ncu"] = facts.get("issue_active_pct")
+    else:
+        roofline["traffic"] = None
+        roofline["traffic_note"] = why
     # the binding resource next to it: the FP64 pipe, against a measured DFMA loop
-    try:
-        fp64_peak = float(L.peaq_b200_fp64_peak_tflops(local_rank))
-    except Exception:
-        fp64_peak = -1.0
-    if fp64_peak > 0:
-        roofline["fp64_peak_tflops_measured"] = fp64_peak
-        if MODE == "advanced":
+    if c.fp64_peak > 0 and dom_ms > 0:
+        roofline["fp64_peak_tflops_measured"] = c.fp64_peak
+        flop = None
+        if mode == "advanced":
             # fb_bank_rec_kernel: 384 FMAs per band and 32-sample sub-step, 40 bands, 32 sub-steps
             # and 4 streams per PEAQ frame
             flop = 2.0 * 384 * 40 * 32 * 2 * CHANNELS * frames_rank
-            roofline["fp64_algorithmic_flop_per_launch_set"] = flop
+            roofline["fp64_flop_source"] = "algorithmic: 384 FMA x 40 bands x 32 sub-steps x 4 streams per frame"
+        elif facts.get("fp64_flop_per_frame"):
+            flop = facts["fp64_flop_per_frame"] * frames_rank
+            roofline["fp64_flop_source"] = "executed DFMA x2 + DMUL + DADD per frame from the ncu capture"
+        if flop:
+            roofline["fp64_flop_per_launch_set"] = flop
             roofline["fp64_achieved_tflops"] = flop / (dom_ms / 1e3) / 1e12
-            roofline["fp64_frac"] = roofline["fp64_achieved_tflops"] / fp64_peak
+            roofline["fp64_frac"] = roofline["fp64_achieved_tflops"] / c.fp64_peak
+    res["roofline"] = roofline
 
-    # ---- CPU baseline (N = 1 only): bounded sample on the host cores ------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    # ---- CPU sample + parity of the GPU results against it --------------------------
+    res["cpu_baseline"] = None
+    res["parity"] = None
+    if cpu_pairs > 0:
         cores = os.cpu_count() or 1
-        n_cpu = max(cores, min(PAIRS_PER_GPU, cores * CPU_PAIRS_PER_CORE))
-        fps, fr, busy, wall, kind = run_cpu_sample(n_cpu, cores)
-        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "first %d of %d pairs x %d s, one process per core, %.1f s wall" % (n_cpu, PAIRS_PER_GPU, PAIR_SECONDS, wall)}
+        fps, fr, busy, wall, kind, rows = run_cpu_sample(cpu_pairs, min(cores, cpu_pairs), mode, n_samples)
+        res["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": min(cores, cpu_pairs), "kind": kind,
+                               "sample": "first %d of %d pairs x %d s, one process per core, %.1f s wall"
+                                         % (cpu_pairs, pairs_gpu, seconds, wall)}
+        res["parity"] = parity_block(out, rows, kind, what)
+    barrier(c)
+    return res, out
+
+
+def our_arm(args):
+    c = make_ctx(args)
+    cores = os.cpu_count() or 1
+    single = c.world == 1
+    pairs_gpu = pairs_per_gpu(c.world)
+
+    def cpu_n(mode, cap):
+        # N = 1: the bounded CPU baseline sample; N > 1: a small parity sample only
+        if args.no_cpu_baseline:
+            return 0
+        return max(1, min(cap, cores * CPU_PAIRS_PER_CORE[mode])) if single else min(cap, cores)
+
+    # ---- headline: BASELINE configs[1] (configs[3] at N = 8), basic ----------------------
+    head, _ = measure(c, "basic", pairs_gpu, PAIR_SECONDS, args.steps, args.warmup,
+                      cpu_n("basic", pairs_gpu), max(1, min(args.steps, 3)),
+                      "headline batch: first pairs of the bench workload itself")
+    extra = {}
+    if not args.headline_only:
+        # ---- BASELINE configs[2]: advanced mode, same batch --------------------------------
+        adv, _ = measure(c, "advanced", PAIRS_PER_GPU, PAIR_SECONDS, max(1, min(args.steps, 3)),
+                         min(args.warmup, 3), cpu_n("advanced", PAIRS_PER_GPU), 2,
+                         "advanced batch: first pairs of the bench workload itself")
+        extra["modes"] = {"advanced": adv}
+        # ---- BASELINE configs[4] shape: few long items ---------------------------------------
+        long_res = {}
+        for mode in ("basic", "advanced"):
+            sec = args.long_seconds if mode == "basic" else (args.long_seconds_advanced or args.long_seconds)
+            n_cpu = 0
+            if not args.no_cpu_baseline and sec <= 600:
+                n_cpu = min(LONG_PAIRS_PER_GPU, cores) if single else min(LONG_PAIRS_PER_GPU, cores, 4)
+            r, _ = measure(c, mode, LONG_PAIRS_PER_GPU, sec, 2, 1, n_cpu, 1,
+                           "long items: first pairs of the long-item workload itself")
+            long_res[mode] = r
+        extra["long_items"] = long_res
+
+    if c.rank != 0:
+        if c.dist is not None:
+            c.dist.barrier()
+            c.dist.destroy_process_group()
+        return 0
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": c.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
-        "wall_ms_per_step": wall_ms / args.steps, "nan_odg_pairs": nan_odg,
-        "odg_min": float(np.nanmin(full["odg"])), "odg_max": float(np.nanmax(full["odg"])),
+        "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"], "roofline": head.get("roofline"),
+        "cpu_baseline": head.get("cpu_baseline"), "parity": head.get("parity"),
+        "gather_ms_per_step": head["gather_ms_per_step"], "wall_ms_per_step": head["wall_ms_per_step"],
+        "nan_odg_pairs": head["nan_odg_pairs"], "odg_min": head["odg_min"], "odg_max": head["odg_max"],
+        "kernel_source_hash": kernel_source_hash(),
     }
+    line.update(extra)
+    parities = [("headline", head.get("parity"))]
+    if "modes" in extra:
+        parities.append(("advanced", extra["modes"]["advanced"].get("parity")))
+        parities += [("long_" + m, extra["long_items"][m].get("parity")) for m in ("basic", "advanced")]
+    failed = [name for name, p in parities if p is not None and not p["ok"]]
+    line["parity_failed"] = failed
     print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    if c.dist is not None:
+        c.dist.barrier()
+        c.dist.destroy_process_group()
+    return 3 if failed else 0
 
 
 def main():
@@ -417,19 +614,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="only the headline workload (no modes.advanced / long_items sections)")
     ap.add_argument("--mode", default="basic", choices=["basic", "advanced"],
-                    help="basic = BASELINE configs[1] (default, the headline); advanced = configs[2]")
+                    help="reference arm only: which mode the CPU path runs (default basic = the headline)")
+    ap.add_argument("--long-seconds", type=int, default=600,
+                    help="item length of the long_items section (BASELINE configs[4] is 3600; the default keeps "
+                         "the whole run and its CPU parity sample within minutes)")
+    ap.add_argument("--long-seconds-advanced", type=int, default=0)
     args = ap.parse_args()
-    global MODE
-    MODE = args.mode
     if args.impl == "reference":
         return reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
-               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--mode", args.mode]
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
     return our_arm(args)
 
