@@ -22,7 +22,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Peaq", "Engine", "PeaqError", "Result", "library_path", "load_library",
+__all__ = ["Peaq", "Engine", "MultiEngine", "PeaqError", "Result", "library_path", "load_library",
            "device_count", "synth_pairs_host", "frames_for_samples", "fb_filter_tables", "ABI_SYMBOLS"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,6 +43,9 @@ ABI_SYMBOLS = [
     "peaq_b200_session_set_playback_level", "peaq_b200_session_get_playback_level",
     "peaq_b200_session_set_channels", "peaq_b200_session_push", "peaq_b200_session_finish",
     "peaq_b200_session_get_result", "peaq_b200_fp64_peak_tflops",
+    "peaq_b200_session_snapshot", "peaq_b200_session_restore",
+    "peaq_b200_multi_create", "peaq_b200_multi_destroy", "peaq_b200_multi_device_count",
+    "peaq_b200_multi_run_batch",
 ]
 
 MOV_NAMES_BASIC = ["BandwidthRefB", "BandwidthTestB", "Total NMRB", "WinModDiff1B", "ADBB", "EHSB",
@@ -82,7 +85,9 @@ class _Batch(C.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "libpeaq_b200.so")
+    """libpeaq_b200.so next to this file (PEAQ_B200_LIBRARY overrides it: development aid for
+    comparing two builds of the engine)"""
+    return os.environ.get("PEAQ_B200_LIBRARY") or os.path.join(_HERE, "libpeaq_b200.so")
 
 
 _lib = None
@@ -134,6 +139,13 @@ def load_library():
     L.peaq_b200_session_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.peaq_b200_session_finish.argtypes = [C.c_void_p]
     L.peaq_b200_session_get_result.argtypes = [C.c_void_p, C.POINTER(Result)]
+    if hasattr(L, "peaq_b200_session_snapshot"):   # (an older build loaded through PEAQ_B200_LIBRARY lacks these)
+        L.peaq_b200_session_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.peaq_b200_session_restore.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.peaq_b200_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.peaq_b200_multi_destroy.argtypes = [C.c_void_p]
+        L.peaq_b200_multi_device_count.argtypes = [C.c_void_p]
+        L.peaq_b200_multi_run_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
     _lib = L
     return L
 
@@ -169,10 +181,12 @@ def synth_pairs_host(first_pair, n_pairs, n_samples, channels=2):
 
 def table(advanced, model, which, playback_level=92.0):
     """Constant table of the engine (host code; see peaq_b200_table)."""
+    if model == 2:
+        raise PeaqError("model 2 (filter-bank taps) has its own accessor: fb_filter_tables()")
     buf = np.zeros(128, dtype=np.float64)
     n = load_library().peaq_b200_table(int(advanced), float(playback_level), model, which,
                                        buf.ctypes.data)
-    return buf[:max(n, 0)].copy()
+    return buf[:max(n, 0)].copy()   # n < 0: this model has no such table
 
 
 def fb_filter_tables(band, playback_level=92.0):
@@ -326,6 +340,52 @@ class Engine:
 
 
 
+class MultiEngine:
+    """Batch engine over several GPUs of one process (peaq_b200_multi): contiguous blocks of
+    pairs per device, results gathered into one host array."""
+
+    def __init__(self, devices=None, advanced=False, playback_level=92.0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            _check(self.lib.peaq_b200_multi_create(C.byref(h), None, 0, int(advanced), float(playback_level)))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(self.lib.peaq_b200_multi_create(C.byref(h), arr, len(devices), int(advanced),
+                                                   float(playback_level)))
+        self.h = h
+
+    def device_count(self):
+        return int(self.lib.peaq_b200_multi_device_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.peaq_b200_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_host(self, ref, test, channels, n_samples=None):
+        ref = np.ascontiguousarray(ref, dtype=np.float32)
+        test = np.ascontiguousarray(test, dtype=np.float32)
+        n_pairs, stride = ref.shape
+        b = _Batch()
+        b.n_pairs, b.channels, b.ref, b.test, b.pair_stride = n_pairs, channels, ref.ctypes.data, test.ctypes.data, stride
+        ns = None
+        if n_samples is not None:
+            ns = np.ascontiguousarray(n_samples, dtype=np.uint64)
+            b.n_samples = ns.ctypes.data
+        b.n_samples_all = stride // channels
+        b.on_device = 0
+        out = np.zeros(n_pairs, dtype=RESULT_DTYPE)
+        _check(self.lib.peaq_b200_multi_run_batch(self.h, C.byref(b), out.ctypes.data))
+        return out
+
+
 class Peaq:
     """One `peaq` element instance (struct _GstPeaq, gstpeaq.c:110-139)."""
 
@@ -413,6 +473,25 @@ class Peaq:
     def chain_test(self, buf):
         """buffer on the `test` sink pad"""
         self._chain(1, buf)
+
+    def snapshot(self):
+        """bytes holding the whole state of the running session (peaq_b200_session_snapshot)"""
+        n = C.c_size_t()
+        _check(self.lib.peaq_b200_session_snapshot(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(self.lib.peaq_b200_session_snapshot(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def restore(self, blob):
+        """continue from a snapshot (possibly taken by another session / process)"""
+        _check(self.lib.peaq_b200_session_restore(self.h, blob, len(blob)))
+        r = Result()
+        self._channels = 0
+        # mode and channels come from the snapshot
+        import struct
+        _, _, adv, ch = struct.unpack_from("<IIii", blob, 0)
+        self._advanced = bool(adv)
+        self._channels = ch
 
     def stop(self):
         """PAUSED->READY: flush the last partial frame and evaluate

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "peaq_engine.h"
@@ -174,6 +175,8 @@ struct Engine {
   RecordLayout last_layout = {};
   size_t last_records_doubles = 0;
   size_t record_budget_bytes = (size_t)16 << 30;
+  int sm_count = 148;
+  int fused_mode = 0;    // PEAQ_B200_FUSED=1: the fused persistent kernel for basic-mode batches
 
   int init() {
     PEAQ_CUDA(cudaSetDevice(device));
@@ -195,6 +198,8 @@ struct Engine {
     build_tables(h_tables, advanced, level);
     PEAQ_CUDA(cudaMalloc(&d_tables, sizeof(DeviceTables)));
     PEAQ_CUDA(cudaMemcpy(d_tables, h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice));
+    PEAQ_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (const char* env = std::getenv("PEAQ_B200_FUSED")) fused_mode = std::atoi(env) ? 1 : 0;
     if (const char* env = std::getenv("PEAQ_B200_RECORD_BUDGET_MB")) {
       const long mb = std::atol(env);
       if (mb > 0) record_budget_bytes = (size_t)mb << 20;
@@ -207,6 +212,17 @@ struct Engine {
       const long mb = std::atol(env);
       if (mb >= 0) hp_whole_budget_bytes = (size_t)mb << 20;
     }
+    return 0;
+  }
+
+  // property `playback_level` on a live model (gstpeaq.c:509-514 sets it on both ear models at any
+  // time, without touching their state): rebuild the tables, keep everything else
+  int set_level(double new_level) {
+    PEAQ_CUDA(cudaSetDevice(device));
+    PEAQ_CUDA(cudaStreamSynchronize(stream));
+    level = new_level;
+    build_tables(h_tables, advanced, level);
+    PEAQ_CUDA(cudaMemcpy(d_tables, h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice));
     return 0;
   }
 
@@ -285,6 +301,7 @@ struct Engine {
   int ensure_stage(int slot, size_t floats) {
     if (floats <= stage_cap[slot]) return 0;
     size_t c0 = stage_cap[slot], c1 = stage_cap[slot];
+    stage_cap[slot] = 0;   // stays 0 if either allocation fails (one buffer may be gone then)
     int rc;
     if ((rc = ensure(&d_stage[slot][0], &c0, std::max<size_t>(floats, 4)))) return rc;
     if ((rc = ensure(&d_stage[slot][1], &c1, std::max<size_t>(floats, 4)))) return rc;
@@ -420,11 +437,27 @@ struct Engine {
         PEAQ_CUDA(cudaGetLastError());
         launches++;
       }
-      rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first, unsigned n) {
-        return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_res,
-                                 n_pairs, stream);
-      });
-      if (rc) return rc;
+      // Two paths, same arithmetic, same bits (tests/test_gpu_parity.py):
+      //  - frame-parallel K1 + per-pair K2 over chunks of per-frame records (default), and
+      //  - PEAQ_B200_FUSED=1: the fused persistent kernel, one CTA per pair, nothing per-frame
+      //    through HBM (DRAM traffic 16.8 KB per frame against 27 KB) -- measured SLOWER on B200
+      //    (6.5 against 8.9 M frames/s at 4096 pairs): a CTA serialises the two halves of a frame
+      //    and its 240 KB of code thrash the instruction caches, so it is opt-in.
+      const bool fused = fused_mode == 1 && !keep_records;
+      if (fused && !keep_records) {
+        if ((rc = timer_begin(1))) return rc;
+        PEAQ_CUDA(launch_fused_basic(d_tables, pcm, n_pairs, 0, std::max(max_frames, 1u), d_state, S, d_res, stream));
+        launches++;
+        if ((rc = timer_end())) return rc;
+        last_layout = L;
+        last_records_doubles = 0;
+      } else {
+        rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first, unsigned n) {
+          return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_res,
+                                   n_pairs, stream);
+        });
+        if (rc) return rc;
+      }
     } else {
       if ((rc = upload_plan(fb, n_pairs, 1))) return rc;
       const PcmView pcm_fb = make_view(d_ref_fb ? d_ref_fb : d_ref, d_test_fb ? d_test_fb : d_test,
@@ -568,13 +601,39 @@ static int check_channels(int channels) {
   return 0;
 }
 
+// owners for the few CUDA objects run_batch creates: every early return releases them
+struct ScopedEvent {
+  cudaEvent_t ev = nullptr;
+  ~ScopedEvent() { if (ev) cudaEventDestroy(ev); }
+};
+struct ScopedDeviceMem {
+  void* p = nullptr;
+  ~ScopedDeviceMem() { if (p) cudaFree(p); }
+};
+// a failed batch must not leave half-recorded timers or pinned plan copies behind (the next
+// successful batch would read an event pair whose end was never recorded)
+struct BatchCleanup {
+  Engine* e;
+  bool ok = false;
+  ~BatchCleanup() {
+    if (ok) return;
+    cudaStreamSynchronize(e->stream);
+    cudaStreamSynchronize(e->copy_stream);
+    e->events_used = 0;
+    e->plan_hold_ns.clear();
+    e->plan_hold_nf.clear();
+    cudaGetLastError();
+  }
+};
+
 static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out) {
   if (!e || !b || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   if (b->n_pairs <= 0) return fail(PEAQ_B200_ERR_INVALID, "n_pairs must be positive");
   int rc = check_channels(b->channels);
   if (rc) return rc;
   if (!b->ref || !b->test) return fail(PEAQ_B200_ERR_INVALID, "null PCM pointer");
-  PEAQ_CUDA(cudaSetDevice(e->device));
+  if (b->on_device && ((reinterpret_cast<uintptr_t>(b->ref) | reinterpret_cast<uintptr_t>(b->test)) & 15))
+    return fail(PEAQ_B200_ERR_INVALID, "device PCM pointers must be 16-byte aligned");
   const int C = b->channels;
   const int n_pairs = b->n_pairs;
   std::vector<uint64_t> ns(n_pairs);
@@ -590,16 +649,17 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     if (n_pairs > 1 && ns[p] * C > b->pair_stride)
       return fail(PEAQ_B200_ERR_INVALID, "pair_stride smaller than an item");
   }
+  PEAQ_CUDA(cudaSetDevice(e->device));
   for (int i = 0; i < 8; i++) e->ms[i] = 0;
-  cudaEvent_t t0, t1;
-  PEAQ_CUDA(cudaEventCreate(&t0));
-  PEAQ_CUDA(cudaEventCreate(&t1));
-  PEAQ_CUDA(cudaEventRecord(t0, e->stream));
+  e->events_used = 0;
+  BatchCleanup cleanup{e};
+  ScopedEvent t0, t1;
+  PEAQ_CUDA(cudaEventCreate(&t0.ev));
+  PEAQ_CUDA(cudaEventCreate(&t1.ev));
+  PEAQ_CUDA(cudaEventRecord(t0.ev, e->stream));
 
   PairResult* res = reinterpret_cast<PairResult*>(out);
   if (b->on_device) {
-    if ((reinterpret_cast<uintptr_t>(b->ref) | reinterpret_cast<uintptr_t>(b->test)) & 15)
-      return fail(PEAQ_B200_ERR_INVALID, "device PCM pointers must be 16-byte aligned");
     const Engine::ClockPlan fft{ns.data(), ns.data(), nf.data()}, fb{ns.data(), ns.data(), nfb.data()};
     rc = e->process_resident(b->ref, b->test, b->pair_stride, n_pairs, C, fft, fb, true, res);
     if (rc) return rc;
@@ -611,8 +671,9 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     const int per_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, slot_budget / std::max<size_t>(stride, 1)));
     // Sub-batch sizes.  Basic mode is bound by the copies (16 KB of PCM per frame against
     // ~100 ns of kernels), so the job takes all copies plus the kernels of the LAST sub-batch:
-    // small, equal sub-batches (one wave of scan CTAs).  Advanced mode is bound by the kernels,
-    // so it takes the FIRST copy plus all kernels: a small first sub-batch, then large ones.
+    // small, equal sub-batches (one wave of the scan kernel's CTAs, two per SM).  Advanced mode
+    // is bound by the kernels, so it takes the FIRST copy plus all kernels: a small first
+    // sub-batch, then large ones.
     std::vector<int> sizes;
     {
       int left = n_pairs;
@@ -621,7 +682,7 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
         sizes.push_back(std::min(per_max, 128));
         left -= sizes.back();
       }
-      const int per = std::min(per_max, e->advanced ? 1024 : 296);
+      const int per = std::min(per_max, e->advanced ? 1024 : (e->fused_mode == 1 ? 3 : 2) * e->sm_count);
       while (left > 0) {
         // basic mode: the very last sub-batches small, the job ends with their kernels
         const int n = (!e->advanced && left <= per) ? std::min(left, 128) : std::min(per, left);
@@ -629,18 +690,30 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
         left -= n;
       }
     }
-    PairResult* d_all = nullptr;
-    PEAQ_CUDA(cudaMalloc(&d_all, (size_t)n_pairs * sizeof(PairResult)));
+    // size everything once, for the largest sub-batch: growing later would free memory under
+    // queued kernels (cudaFree synchronises the device and stalls the copy / compute overlap)
+    {
+      const int np_max = *std::max_element(sizes.begin(), sizes.end());
+      const StateLayout S = make_state_layout(C, e->h_tables->fft_bands);
+      const AdvStateLayout A = make_adv_state_layout(C);
+      if ((rc = e->ensure_pairs((size_t)np_max, e->advanced ? (size_t)A.stride : (size_t)S.stride, false))) return rc;
+    }
+    ScopedDeviceMem d_all_mem;
+    PEAQ_CUDA(cudaMalloc(&d_all_mem.p, (size_t)n_pairs * sizeof(PairResult)));
+    PairResult* d_all = static_cast<PairResult*>(d_all_mem.p);
     int p0 = 0;
     for (int i = 0; i < (int)sizes.size(); p0 += sizes[i], i++) {
       const int np = sizes[i];
       const int slot = i & 1;
-      const size_t floats = (size_t)(np - 1) * stride + (size_t)max_n * C;
+      // the caller's arrays end with the last pair's samples: never read past them
+      const size_t floats = (size_t)(np - 1) * stride + (size_t)ns[p0 + np - 1] * C;
+      // (pairs before the last one are read up to the stride; the kernels read ns[p] samples)
       if (i >= 2) PEAQ_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_freed[slot], 0));
-      if (floats > e->stage_cap[slot]) {
+      const size_t need = (size_t)(np - 1) * stride + (size_t)max_n * C;   // same capacity for every sub-batch
+      if (need > e->stage_cap[slot]) {
         // growing a slot frees memory that queued kernels may still read: drain first
         PEAQ_CUDA(cudaStreamSynchronize(e->stream));
-        if ((rc = e->ensure_stage(slot, floats))) return rc;
+        if ((rc = e->ensure_stage(slot, need))) return rc;
       }
       if (floats) {
         PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[slot][0], b->ref + (size_t)p0 * stride, floats * sizeof(float),
@@ -654,29 +727,52 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
           fb{ns.data() + p0, ns.data() + p0, nfb.data() + p0};
       rc = e->process_resident(e->d_stage[slot][0], e->d_stage[slot][1], stride, np, C, fft, fb, true, nullptr,
                                d_all + p0, false);
-      if (rc) {
-        cudaFree(d_all);
-        return rc;
-      }
+      if (rc) return rc;
       PEAQ_CUDA(cudaEventRecord(e->ev_freed[slot], e->stream));
     }
     PEAQ_CUDA(cudaMemcpyAsync(res, d_all, (size_t)n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost, e->stream));
     rc = e->finish_batch();
-    cudaFree(d_all);
     if (rc) return rc;
   }
-  PEAQ_CUDA(cudaEventRecord(t1, e->stream));
-  PEAQ_CUDA(cudaEventSynchronize(t1));
+  PEAQ_CUDA(cudaEventRecord(t1.ev, e->stream));
+  PEAQ_CUDA(cudaEventSynchronize(t1.ev));
   float t = 0;
-  PEAQ_CUDA(cudaEventElapsedTime(&t, t0, t1));
+  PEAQ_CUDA(cudaEventElapsedTime(&t, t0.ev, t1.ev));
   e->ms[0] = t;
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
+  cleanup.ok = true;
   return 0;
 }
 
 // ---------------------------------------------------------------------------
 // session = one element instance
+
+// GstAdapter stand-in: append at the back, take from the front.  Consuming advances a read
+// offset; the storage is compacted only when more than half of it is dead.
+struct Fifo {
+  std::vector<float> buf;
+  size_t head = 0;
+  size_t size() const { return buf.size() - head; }
+  bool empty() const { return size() == 0; }
+  const float* data() const { return buf.data() + head; }
+  void append(const float* p, size_t n) {
+    if (head && head >= buf.size() / 2) {
+      buf.erase(buf.begin(), buf.begin() + head);
+      head = 0;
+    }
+    buf.insert(buf.end(), p, p + n);
+  }
+  void consume(size_t n) {
+    head += n;
+    if (head >= buf.size()) {
+      buf.clear();
+      head = 0;
+    }
+  }
+  void clear() {
+    buf.clear();
+    head = 0;
+  }
+};
 
 struct Session {
   int device = 0;
@@ -687,24 +783,55 @@ struct Session {
   bool started = false;          // recurrent state initialised on the device
   // GstAdapter stand-ins: [0] FFT clock (ref_adapter_fft / test_adapter_fft), [1] filter-bank
   // clock (ref_adapter_fb / test_adapter_fb, advanced mode only; gstpeaq.c:116-119, :626-635)
-  std::vector<float> fifo[2][2];   // [clock][ref|test]
+  Fifo fifo[2][2];   // [clock][ref|test]
   PairResult last = {};
   bool have_result = false;
+  // Streaming without stalling the caller (the element's streaming thread, gstpeaq.c:614-661): a
+  // push copies the frames that became complete into one of two PINNED staging sets, queues the
+  // copy to the device and the kernels on the engine's stream, and returns.  Nothing waits for the
+  // GPU until a result is read (properties odg / di / totalsnr, gstpeaq.c:484-497), the session is
+  // finished or snapshotted, or kMaxPending pushes are in flight.
+  static constexpr int kMaxPending = 64;
+  float* pin[2][2][2] = {};          // [set][clock][ref|test]
+  size_t pin_cap[2][2] = {};         // floats per buffer of [set][clock]
+  cudaEvent_t pin_done[2] = {nullptr, nullptr};
+  bool pin_used[2] = {false, false};
+  int pin_next = 0;
+  int pending = 0;                   // pushes queued since the last synchronisation
+  bool result_stale = false;         // the device holds a newer result than `last`
 
   void reset_stream() {
+    sync();
     started = false;
     have_result = false;
+    result_stale = false;
     for (auto& c : fifo)
       for (auto& f : c) f.clear();
   }
 
+  void free_pinned() {
+    for (int i = 0; i < 2; i++) {
+      for (int c = 0; c < 2; c++) {
+        for (int sd = 0; sd < 2; sd++) {
+          if (pin[i][c][sd]) cudaFreeHost(pin[i][c][sd]);
+          pin[i][c][sd] = nullptr;
+        }
+        pin_cap[i][c] = 0;
+      }
+      if (pin_done[i]) cudaEventDestroy(pin_done[i]);
+      pin_done[i] = nullptr;
+      pin_used[i] = false;
+    }
+  }
+
   void drop_engine() {
+    reset_stream();
     if (engine) {
       engine->destroy();
       delete engine;
       engine = nullptr;
     }
-    reset_stream();
+    free_pinned();
   }
 
   int ensure_engine() {
@@ -723,38 +850,84 @@ struct Session {
     return rc;
   }
 
-  int stage(int slot, const float* ref, const float* test, size_t floats) {
-    int rc;
-    if ((rc = engine->ensure_stage(slot, floats))) return rc;
-    if (floats) {
-      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[slot][0], ref, floats * sizeof(float), cudaMemcpyHostToDevice,
-                                engine->stream));
-      PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[slot][1], test, floats * sizeof(float), cudaMemcpyHostToDevice,
-                                engine->stream));
-    }
+  // waits for everything queued so far; afterwards plan copies and timers are collected
+  int sync() {
+    if (!engine || pending == 0) return 0;
+    pending = 0;
+    PEAQ_CUDA(cudaSetDevice(device));
+    return engine->finish_batch();
+  }
+
+  // latest result on the host
+  int fetch_result() {
+    if (!result_stale) return 0;
+    PEAQ_CUDA(cudaSetDevice(device));
+    PEAQ_CUDA(cudaMemcpyAsync(&last, engine->d_results, sizeof(PairResult), cudaMemcpyDeviceToHost, engine->stream));
+    pending++;
+    int rc = sync();
+    if (rc) return rc;
+    result_stale = false;
     return 0;
   }
 
-  // Runs k_fft frames of the FFT clock over the first n_fft samples of (ref_fft, test_fft)
+  // copies `floats` of each signal into pinned set `set` and queues the transfer to the device slot
+  int stage(int set, int clock, const float* ref, const float* test, size_t floats) {
+    int rc;
+    if ((rc = engine->ensure_stage(clock, floats))) return rc;
+    if (!floats) return 0;
+    if (floats > pin_cap[set][clock]) {
+      const size_t cap = std::max<size_t>(floats, (size_t)4096 * channels);
+      for (int sd = 0; sd < 2; sd++) {
+        if (pin[set][clock][sd]) PEAQ_CUDA(cudaFreeHost(pin[set][clock][sd]));
+        pin[set][clock][sd] = nullptr;
+      }
+      pin_cap[set][clock] = 0;
+      for (int sd = 0; sd < 2; sd++) PEAQ_CUDA(cudaHostAlloc((void**)&pin[set][clock][sd], cap * sizeof(float), cudaHostAllocDefault));
+      pin_cap[set][clock] = cap;
+    }
+    std::memcpy(pin[set][clock][0], ref, floats * sizeof(float));
+    std::memcpy(pin[set][clock][1], test, floats * sizeof(float));
+    PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[clock][0], pin[set][clock][0], floats * sizeof(float),
+                              cudaMemcpyHostToDevice, engine->stream));
+    PEAQ_CUDA(cudaMemcpyAsync(engine->d_stage[clock][1], pin[set][clock][1], floats * sizeof(float),
+                              cudaMemcpyHostToDevice, engine->stream));
+    return 0;
+  }
+
+  // Queues k_fft frames of the FFT clock over the first n_fft samples of (ref_fft, test_fft)
   // and k_fb frames of the filter-bank clock over the first n_fb samples of (ref_fb, test_fb),
-  // continuing from the state on the device.
+  // continuing from the state on the device.  The host buffers are free again on return.
   int run_frames(unsigned k_fft, const float* ref_fft, const float* test_fft, size_t n_fft, unsigned k_fb,
                  const float* ref_fb, const float* test_fb, size_t n_fb) {
     int rc = ensure_engine();
     if (rc) return rc;
     PEAQ_CUDA(cudaSetDevice(device));
     const size_t fl_fft = n_fft * channels, fl_fb = n_fb * channels;
-    if ((rc = stage(0, ref_fft, test_fft, fl_fft))) return rc;
-    if (advanced && (rc = stage(1, ref_fb, test_fb, fl_fb))) return rc;
+    // growing a device slot or a pinned set frees memory queued work may still use: drain first
+    const int set = pin_next;
+    pin_next ^= 1;
+    if (fl_fft > engine->stage_cap[0] || (advanced && fl_fb > engine->stage_cap[1]) || fl_fft > pin_cap[set][0] ||
+        (advanced && fl_fb > pin_cap[set][1])) {
+      if ((rc = sync())) return rc;
+      PEAQ_CUDA(cudaStreamSynchronize(engine->stream));
+    }
+    if (!pin_done[set]) PEAQ_CUDA(cudaEventCreateWithFlags(&pin_done[set], cudaEventDisableTiming));
+    if (pin_used[set]) PEAQ_CUDA(cudaEventSynchronize(pin_done[set]));   // the copy issued two pushes ago
+    if ((rc = stage(set, 0, ref_fft, test_fft, fl_fft))) return rc;
+    if (advanced && (rc = stage(set, 1, ref_fb, test_fb, fl_fb))) return rc;
+    PEAQ_CUDA(cudaEventRecord(pin_done[set], engine->stream));
+    pin_used[set] = true;
     const uint64_t ns_fft = n_fft, ns_fb = n_fb;
     const Engine::ClockPlan fft{&ns_fft, &ns_fft, &k_fft}, fb{&ns_fb, &ns_fb, &k_fb};
     rc = engine->process_resident(engine->d_stage[0][0], engine->d_stage[0][1], std::max<size_t>(fl_fft, 1), 1,
-                                  channels, fft, fb, !started, &last, nullptr, true,
+                                  channels, fft, fb, !started, nullptr, nullptr, false,
                                   advanced ? engine->d_stage[1][0] : nullptr,
                                   advanced ? engine->d_stage[1][1] : nullptr, std::max<size_t>(fl_fb, 1));
     if (rc) return rc;
     started = true;
     have_result = true;
+    result_stale = true;
+    if (++pending >= kMaxPending) return sync();
     return 0;
   }
 
@@ -773,7 +946,7 @@ struct Session {
 
   void consume(int clock, unsigned k, unsigned St) {
     const size_t n = (size_t)k * St * channels;
-    for (int s = 0; s < 2; s++) fifo[clock][s].erase(fifo[clock][s].begin(), fifo[clock][s].begin() + n);
+    for (int s = 0; s < 2; s++) fifo[clock][s].consume(n);
   }
 
   // pad_chain's processing part (gstpeaq.c:637-656): drain both clocks
@@ -802,14 +975,123 @@ struct Session {
       for (int s = 0; s < 2; s++) {
         pad[c][s].assign(frame, 0.f);
         const size_t n = std::min(fifo[c][s].size(), frame);
-        std::copy(fifo[c][s].begin(), fifo[c][s].begin() + n, pad[c][s].begin());
-        fifo[c][s].erase(fifo[c][s].begin(), fifo[c][s].begin() + n);
+        std::copy(fifo[c][s].data(), fifo[c][s].data() + n, pad[c][s].begin());
+        fifo[c][s].consume(n);
       }
       k[c] = 1;
     }
     if (!k[0] && !k[1]) return 0;
     return run_frames(k[0], pad[0][0].data(), pad[0][1].data(), k[0] ? kFftFrame : 0, k[1], pad[1][0].data(),
                       pad[1][1].data(), k[1] ? kFbFrame : 0);
+  }
+
+  // ---- snapshot / restore ------------------------------------------------------------------
+  // Layout: SnapHeader | 4 FIFO contents (float) | device state block (double) | DC-reject and
+  // filter-bank chain state (double, advanced) | last result
+  struct SnapHeader {
+    uint32_t magic, version;
+    int32_t advanced, channels, started, have_result;
+    double level;
+    uint64_t fifo_floats[2][2];
+    uint64_t state_doubles, hp_doubles;
+  };
+  static constexpr uint32_t kSnapMagic = 0x51414550u;   // "PEAQ"
+
+  size_t state_doubles() const {
+    if (!started) return 0;
+    const int B = engine->h_tables->fft_bands;
+    return advanced ? (size_t)make_adv_state_layout(channels).stride : (size_t)make_state_layout(channels, B).stride;
+  }
+  size_t hp_doubles() const { return started && advanced ? (size_t)2 * channels * kHpStateDoubles : 0; }
+
+  int snapshot(void* buf, size_t capacity, size_t* size) {
+    int rc = fetch_result();
+    if (rc) return rc;
+    if ((rc = sync())) return rc;
+    SnapHeader h = {};
+    h.magic = kSnapMagic;
+    h.version = 1;
+    h.advanced = advanced;
+    h.channels = channels;
+    h.started = started;
+    h.have_result = have_result;
+    h.level = level;
+    size_t total = sizeof h;
+    for (int c = 0; c < 2; c++)
+      for (int sd = 0; sd < 2; sd++) {
+        h.fifo_floats[c][sd] = fifo[c][sd].size();
+        total += fifo[c][sd].size() * sizeof(float);
+      }
+    h.state_doubles = state_doubles();
+    h.hp_doubles = hp_doubles();
+    total += (h.state_doubles + h.hp_doubles) * sizeof(double) + sizeof(PairResult);
+    if (size) *size = total;
+    if (!buf) return 0;
+    if (capacity < total) return fail(PEAQ_B200_ERR_INVALID, "snapshot buffer too small");
+    unsigned char* p = static_cast<unsigned char*>(buf);
+    std::memcpy(p, &h, sizeof h);
+    p += sizeof h;
+    for (int c = 0; c < 2; c++)
+      for (int sd = 0; sd < 2; sd++) {
+        std::memcpy(p, fifo[c][sd].data(), fifo[c][sd].size() * sizeof(float));
+        p += fifo[c][sd].size() * sizeof(float);
+      }
+    if (h.state_doubles) {
+      PEAQ_CUDA(cudaSetDevice(device));
+      PEAQ_CUDA(cudaStreamSynchronize(engine->stream));
+      PEAQ_CUDA(cudaMemcpy(p, engine->d_state, h.state_doubles * sizeof(double), cudaMemcpyDeviceToHost));
+      p += h.state_doubles * sizeof(double);
+      if (h.hp_doubles) {
+        PEAQ_CUDA(cudaMemcpy(p, engine->d_hp_state, h.hp_doubles * sizeof(double), cudaMemcpyDeviceToHost));
+        p += h.hp_doubles * sizeof(double);
+      }
+    }
+    std::memcpy(p, &last, sizeof(PairResult));
+    return 0;
+  }
+
+  int restore(const void* buf, size_t size) {
+    if (size < sizeof(SnapHeader)) return fail(PEAQ_B200_ERR_INVALID, "not a session snapshot");
+    SnapHeader h;
+    std::memcpy(&h, buf, sizeof h);
+    if (h.magic != kSnapMagic || h.version != 1) return fail(PEAQ_B200_ERR_INVALID, "not a session snapshot");
+    if (h.channels < 0 || h.channels > kMaxChannels) return fail(PEAQ_B200_ERR_INVALID, "corrupt snapshot");
+    size_t total = sizeof h + (h.state_doubles + h.hp_doubles) * sizeof(double) + sizeof(PairResult);
+    for (int c = 0; c < 2; c++)
+      for (int sd = 0; sd < 2; sd++) total += h.fifo_floats[c][sd] * sizeof(float);
+    if (size < total) return fail(PEAQ_B200_ERR_INVALID, "truncated snapshot");
+    drop_engine();
+    advanced = h.advanced != 0;
+    level = h.level;
+    channels = h.channels;
+    const unsigned char* p = static_cast<const unsigned char*>(buf) + sizeof h;
+    for (int c = 0; c < 2; c++)
+      for (int sd = 0; sd < 2; sd++) {
+        fifo[c][sd].append(reinterpret_cast<const float*>(p), h.fifo_floats[c][sd]);
+        p += h.fifo_floats[c][sd] * sizeof(float);
+      }
+    if (h.started) {
+      int rc = ensure_engine();
+      if (rc) return rc;
+      PEAQ_CUDA(cudaSetDevice(device));
+      started = true;
+      if (h.state_doubles != state_doubles() || h.hp_doubles != hp_doubles()) {
+        started = false;
+        return fail(PEAQ_B200_ERR_INVALID, "snapshot of another engine version");
+      }
+      if ((rc = engine->ensure_pairs(1, h.state_doubles, false))) return rc;
+      PEAQ_CUDA(cudaMemcpy(engine->d_state, p, h.state_doubles * sizeof(double), cudaMemcpyHostToDevice));
+      p += h.state_doubles * sizeof(double);
+      if (h.hp_doubles) {
+        if ((rc = engine->ensure(&engine->d_hp_state, &engine->hp_state_cap, (size_t)h.hp_doubles))) return rc;
+        PEAQ_CUDA(cudaMemcpy(engine->d_hp_state, p, h.hp_doubles * sizeof(double), cudaMemcpyHostToDevice));
+        p += h.hp_doubles * sizeof(double);
+      }
+    }
+    std::memcpy(&last, p, sizeof(PairResult));
+    have_result = h.have_result != 0;
+    result_stale = false;
+    return 0;
   }
 };
 
@@ -1115,8 +1397,12 @@ int peaq_b200_session_set_playback_level(peaq_b200_session* h, double level_db) 
   if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   if (!(level_db >= 0. && level_db <= 130.)) return fail(PEAQ_B200_ERR_INVALID, "playback level out of range");
   Session* s = reinterpret_cast<Session*>(h);
-  if (s->started) return fail(PEAQ_B200_ERR_INVALID, "playback level cannot change mid-stream");
-  s->drop_engine();
+  if (s->engine) {
+    // like the reference (gstpeaq.c:509-514): takes effect from the next frame, state is kept
+    int rc = s->sync();
+    if (rc) return rc;
+    if ((rc = s->engine->set_level(level_db))) return rc;
+  }
   s->level = level_db;
   return 0;
 }
@@ -1143,8 +1429,8 @@ int peaq_b200_session_push(peaq_b200_session* h, int pad, const float* data, siz
   if (pad != PEAQ_B200_PAD_REF && pad != PEAQ_B200_PAD_TEST) return fail(PEAQ_B200_ERR_INVALID, "bad pad");
   Session* s = reinterpret_cast<Session*>(h);
   if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
-  s->fifo[0][pad].insert(s->fifo[0][pad].end(), data, data + n * s->channels);
-  if (s->advanced) s->fifo[1][pad].insert(s->fifo[1][pad].end(), data, data + n * s->channels);
+  s->fifo[0][pad].append(data, n * s->channels);
+  if (s->advanced) s->fifo[1][pad].append(data, n * s->channels);
   return s->drain();
 }
 
@@ -1154,7 +1440,8 @@ int peaq_b200_session_finish(peaq_b200_session* h) {
   if (s->channels == 0) return fail(PEAQ_B200_ERR_INVALID, "channels not negotiated");
   int rc = s->drain();
   if (rc) return rc;
-  return s->flush();
+  if ((rc = s->flush())) return rc;
+  return s->fetch_result();
 }
 
 int peaq_b200_session_get_result(peaq_b200_session* h, peaq_b200_result* out) {
@@ -1171,7 +1458,93 @@ int peaq_b200_session_get_result(peaq_b200_session* h, peaq_b200_result* out) {
     out->loudness_reached_frame = UINT_MAX;
     return 0;
   }
+  int rc = s->fetch_result();   // waits for the pushes queued so far
+  if (rc) return rc;
   std::memcpy(out, &s->last, sizeof *out);
+  return 0;
+}
+
+int peaq_b200_session_snapshot(peaq_b200_session* h, void* buf, size_t capacity, size_t* size) {
+  if (!h) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  return reinterpret_cast<Session*>(h)->snapshot(buf, capacity, size);
+}
+
+int peaq_b200_session_restore(peaq_b200_session* h, const void* buf, size_t size) {
+  if (!h || !buf) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  return reinterpret_cast<Session*>(h)->restore(buf, size);
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU batch: one engine and one host thread per device, contiguous blocks of pairs
+
+struct peaq_b200_multi {
+  std::vector<Engine*> engines;
+};
+
+int peaq_b200_multi_create(peaq_b200_multi** out, const int* devices, int n_devices, int advanced,
+                           double playback_level) {
+  if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int visible = peaq_b200_device_count();
+  if (n_devices <= 0) n_devices = visible;
+  if (n_devices <= 0) return fail(PEAQ_B200_ERR_CUDA, "no CUDA device (the engine has no CPU fallback)");
+  peaq_b200_multi* m = new (std::nothrow) peaq_b200_multi;
+  if (!m) return fail(PEAQ_B200_ERR_NOMEM, "out of host memory");
+  for (int i = 0; i < n_devices; i++) {
+    const int dev = devices ? devices[i] : i;
+    peaq_b200_engine* e = nullptr;
+    int rc = peaq_b200_engine_create(&e, dev, advanced, playback_level);
+    if (rc) {
+      peaq_b200_multi_destroy(m);
+      return rc;
+    }
+    m->engines.push_back(reinterpret_cast<Engine*>(e));
+  }
+  *out = m;
+  return 0;
+}
+
+int peaq_b200_multi_destroy(peaq_b200_multi* m) {
+  if (!m) return 0;
+  for (Engine* e : m->engines) peaq_b200_engine_destroy(reinterpret_cast<peaq_b200_engine*>(e));
+  delete m;
+  return 0;
+}
+
+int peaq_b200_multi_device_count(const peaq_b200_multi* m) { return m ? (int)m->engines.size() : 0; }
+
+int peaq_b200_multi_run_batch(peaq_b200_multi* m, const peaq_b200_batch* b, peaq_b200_result* out) {
+  if (!m || !b || !out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
+  if (b->on_device) return fail(PEAQ_B200_ERR_INVALID, "the multi-GPU batch takes host buffers");
+  if (b->n_pairs <= 0) return fail(PEAQ_B200_ERR_INVALID, "n_pairs must be positive");
+  const int n_dev = (int)m->engines.size();
+  std::vector<int> rcs(n_dev, 0);
+  std::vector<std::string> errs(n_dev);
+  std::vector<std::thread> workers;
+  const int base = b->n_pairs / n_dev, rem = b->n_pairs % n_dev;
+  int first = 0;
+  for (int d = 0; d < n_dev; d++) {
+    const int count = base + (d < rem ? 1 : 0);
+    if (count > 0) {
+      peaq_b200_batch sub = *b;
+      sub.n_pairs = count;
+      // a single pair is addressed without a stride (see run_batch): hand over explicit pointers
+      const size_t stride = b->n_pairs > 1 ? b->pair_stride : 0;
+      sub.ref = b->ref + (size_t)first * stride;
+      sub.test = b->test + (size_t)first * stride;
+      if (b->n_samples) sub.n_samples = b->n_samples + first;
+      if (count == 1 && b->n_pairs > 1) sub.pair_stride = b->pair_stride;
+      peaq_b200_result* dst = out + first;
+      workers.emplace_back([&, d, sub, dst]() {
+        rcs[d] = run_batch(m->engines[d], &sub, dst);   // the D2H of this device's rows IS the gather
+        if (rcs[d]) errs[d] = g_last_error;              // thread-local: hand it to the caller's thread
+      });
+    }
+    first += count;
+  }
+  for (auto& w : workers) w.join();
+  for (int d = 0; d < n_dev; d++)
+    if (rcs[d]) return fail(rcs[d], "device " + std::to_string(m->engines[d]->device) + ": " + errs[d]);
   return 0;
 }
 

@@ -148,6 +148,12 @@ cudaError_t launch_scan_basic(const DeviceTables* d_tables, const double* record
 
 size_t fft_frames_smem_bytes(int channels);
 
+// Fused persistent kernel (basic mode): K1 + K2 of one pair in one CTA, frames
+// [first_frame, first_frame + n_chunk_frames); same state block and results as K1 + K2.
+cudaError_t launch_fused_basic(const DeviceTables* d_tables, PcmView pcm, int n_pairs, unsigned first_frame,
+                               unsigned n_chunk_frames, double* state, StateLayout S, PairResult* results,
+                               cudaStream_t stream);
+
 // advanced mode (peaq_fb.cu, peaq_scan_adv.cu)
 cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsigned n_chunk_frames,
                             unsigned char* flags, cudaStream_t stream);

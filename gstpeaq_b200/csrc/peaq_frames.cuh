@@ -1,30 +1,34 @@
-// K1 `fft_frames`: the stateless, frame-parallel half of the PEAQ hot path.
+// Device code of the stateless, frame-parallel half of the PEAQ hot path (`frame_body`), shared by
+// K1 `fft_frames_kernel` (peaq_frames.cu: one CTA per frame, results to per-frame records in HBM)
+// and the fused persistent kernel (peaq_fused.cu: one CTA per pair, results stay in shared memory
+// for the recurrent half of the same frame).
 //
-// One CTA = one FFT-clock frame of one (ref,test) pair; 2*C warps, warp w handles
-// stream (channel c = w/2, side = w%2: 0 ref, 1 test).  Per stream:
-//   PCM (interleaved F32, HBM, 128-bit loads) -> Hann window -> 2048-pt real FFT
+// One CTA = one FFT-clock frame of one (ref,test) pair; 4*C warps, two warps per
+// stream (channel c, side: 0 ref, 1 test).  Per stream:
+//   PCM (interleaved F32, HBM, TMA bulk copy) -> Hann window -> 2048-pt real FFT
 //   (1024-pt complex radix-4 in shared memory + split) -> power spectrum ->
 //   outer/middle-ear weighting -> critical-band grouping -> + internal noise ->
 //   level dependent frequency spreading      (fftearmodel.c:432-515, :603-676)
 // and per channel: noise spectrum grouped into bands (movs.c:988-1000), bandwidth
 // bins (movs.c:776-809), error-harmonic-structure value (movs.c:1346-1443), energy
 // and above-threshold flags (fftearmodel.c:508-514, gstpeaq.c:1081-1099) and the
-// SNR partial sums (gstpeaq.c:913-918).  Everything recurrent is left to K2.
+// SNR partial sums (gstpeaq.c:913-918).  Everything recurrent is left to the scan.
 //
-// Shared memory: 16 KB per warp (the FFT buffer, reused for the weighted power
+// Shared memory: 16 KB per stream (the FFT buffer, reused for the weighted power
 // spectrum and the spreading / EHS scratch) + 8 KB of twiddles => 3 CTAs per SM.
 // The power spectrum is staged in registers between the FFT read-out and the
 // write-back, and the bandwidth decisions are taken on those registers, so the
 // unweighted spectrum never needs its own buffer.
 //
-// Arithmetic is IEEE double; the file is compiled with -fmad=false so that
+// Arithmetic is IEEE double; the including files are compiled with -fmad=false so that
 // expressions restated from the reference round like the reference's (gcc,
 // x86-64, no contraction); fused multiply-adds appear only where written
-// explicitly (FFT butterflies).  Powers x^y of the spreading stage are evaluated
-// as exp(y ln x) with shared logarithms (relative deviation from libm's pow
-// ~1e-15, far inside the 1e-6 parity bar).
+// explicitly (FFT butterflies, the transcendental kernels of peaq_math.cuh).
+#pragma once
+
 #include "peaq_engine.h"
 #include "peaq_fft.cuh"
+#include "peaq_math.cuh"
 
 #include <cstdlib>
 #include <type_traits>
@@ -36,11 +40,14 @@ constexpr int kWorkDoubles = 2048;   // per-warp buffer: 1024 complex points
 constexpr int kTwDoubles = 2 * 512;
 constexpr int kScratchDlog = 1536;   // dlog[512] (test stream's buffer)
 
+#ifndef PEAQ_WARP_SUM_DEFINED
+#define PEAQ_WARP_SUM_DEFINED
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+#endif
 
 __device__ __forceinline__ double warp_max_nonan(double v) {
 #pragma unroll
@@ -133,46 +140,45 @@ __device__ __forceinline__ double noise_bin(const double* spec_ref, const double
   return r - 2 * sqrt(r * t) + t;
 }
 
-__device__ __forceinline__ double group_band_noise(const DeviceTables* __restrict__ T,
-                                                   const double* spec_ref, const double* spec_test,
-                                                   int i) {
-  // wl N[lo] + wu N[hi] + N[lo+1] + ... + N[hi-1] in the reference's order, through one copy of
-  // the (long) square-root code: the inner bins carry weight 1, which multiplies exactly
+// noise_in_bands[i] (movs.c:999-1000): the grouping of fftearmodel.c:603-620 applied to the noise
+// spectrum.  `nz[k]` = noise_bin(k), computed one bin per thread beforehand (the square roots are
+// the cost and band widths range from 1 to ~50 bins, so a lane per band would idle most lanes);
+// the sum runs in the reference's order: wl N[lo] + wu N[hi] + N[lo+1] + ... + N[hi-1].
+__device__ __forceinline__ double group_band_noise(const DeviceTables* __restrict__ T, const double* nz, int i) {
   const int lo = T->band_lo[i], hi = T->band_hi[i];
-  const double wl = T->band_wl[i], wu = T->band_wu[i];
-  double p = 0.;
-  const int n_terms = hi > lo ? hi - lo + 1 : 2;   // both edge terms exist even when lo == hi
-#pragma unroll 1
-  for (int j = 0; j < n_terms; j++) {
-    const int k = j == 0 ? lo : (j == 1 ? hi : lo + j - 1);
-    const double w = j == 0 ? wl : (j == 1 ? wu : 1.);
-    const double v = w * noise_bin(spec_ref, spec_test, k);
-    p = j == 0 ? v : p + v;
-  }
+  double p = T->band_wl[i] * nz[lo];
+  p = p + T->band_wu[i] * nz[hi];   // both edge terms exist even when lo == hi
+  for (int k = lo + 1; k < hi; k++) p = p + nz[k];
   return p < 1e-12 ? 1e-12 : p;
 }
 
-// Level dependent frequency spreading of one stream (do_spreading,
-// fftearmodel.c:636-676).  `se` holds the pitch pattern on entry, the result
-// goes to `out` (global record).  sa/se/se2: warp-private shared arrays.
-__device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* sa, double* se,
-                             double* se2, double* __restrict__ out, int lane) {
+// Level dependent frequency spreading (do_spreading, fftearmodel.c:636-676), in two parts.
+//
+// spread_prepare (one warp per stream): slopes, normalisation and the downward pass.
+// `se` holds the pitch pattern on entry; on return the stream's scratch holds
+//   sa[i] = aUCE[i]^0.4, se[i] = En[i]^0.4, se2[i] = downward-spread pattern (all in the 0.4 domain).
+__device__ void spread_prepare(const DeviceTables* __restrict__ T, int B, double* sa, double* se,
+                               double* se2, int lane) {
   const double dz02 = 0.2 * T->dz;
-  // four bands per lane, interleaved for instruction-level parallelism
+  // four bands per lane
+#if defined(PEAQ_DEV_ROLLED)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int m = 0; m < 4; m++) {
     const int i = lane + 32 * m;
     const int ii = i < B ? i : B - 1;
     // aUCE = aUC * Pp^(0.2 dz); gIU = (1 - aUCE^(B-i)) / (1 - aUCE);
     // En = Pp / (gIL + gIU - 1); store aUCE^0.4 and En^0.4   (:647-656)
     const double pp = i < B ? se[i] : 1.;
-    const double lp = log(pp);
+    const double lp = peaq_log(pp);
     const double la = T->log_aUC[ii] + dz02 * lp;     // ln aUCE
-    const double a_uce = exp(la);
-    const double g_iu = (1. - exp((double)(B - ii) * la)) / (1. - a_uce);
+    const double a_uce = peaq_exp(la);
+    const double g_iu = (1. - peaq_exp((double)(B - ii) * la)) / (1. - a_uce);
     const double den = T->gIL[ii] + g_iu - 1.;
-    const double va = exp(0.4 * la);
-    const double ve = exp(0.4 * (lp - log(den)));
+    const double va = peaq_exp(0.4 * la);
+    const double ve = peaq_exp(0.4 * (lp - peaq_log(den)));
     if (i < B) {   // each lane rewrites only the entry it read
       sa[i] = va;
       se[i] = ve;
@@ -209,11 +215,56 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
     if (4 * lane + 0 < B) se2[4 * lane + 0] = v[0] + a4 * hi;
   }
   __syncwarp();
-  // upward spreading (:664-671): source band i adds Ene[i] * aUCEe[i]^(j-i) to every
-  // j > i.  Lane l owns sources AND targets l + 32 m.  At step t = 32 A + b every lane
-  // advances its sources (r *= a, the only serial chain) and each target fetches the
-  // contribution of source j - t from lane (l - b) mod 32, slot m - A (or m - A - 1 when
-  // the lane index wraps) with a shuffle: no shared memory, no barrier in the loop.
+}
+
+// spread_ladder (one warp per stream): upward spreading (:664-671), source band i adds
+// Ene[i] * aUCEe[i]^(j-i) to every band j > i -- O(B^2 / 2) multiply-adds whose cost is the data
+// movement, not the arithmetic.  A lane owns the four consecutive bands p = 4 l + m as SOURCES
+// (r[m] = running power Ene * a^t, the only multiplications) and four TRAVELLING accumulators:
+// at step t accumulator slot p holds the partial sum of target band p + t, takes its source's
+// term, and moves one slot down.  Inside a lane that move is a register renaming (the loop is
+// unrolled by 4); only slot 0 of each lane crosses to the lane below: ONE shuffle per lane and
+// step instead of one per band, and no per-band select.  The accumulator leaving slot 0 of lane 0
+// at step t is the finished band t.  Every target still receives its terms nearest source first,
+// starting from the downward pattern, each term the same chain of products as before: results are
+// bit for bit those of the one-shuffle-per-band ladder this replaces (13 instead of 26
+// instructions per step).  On return se2[i] holds the complete spread pattern (0.4 domain).
+__device__ void spread_ladder(int B, double* scr, int lane) {
+  const double* sa = scr;
+  const double* se = scr + 128;
+  double* se2 = scr + 256;
+  double r[4], a[4], acc[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const int p = 4 * lane + m;
+    r[m] = p < B ? se[p] : 0.;
+    a[m] = p < B ? sa[p] : 0.;
+    acc[m] = p + 1 < B ? se2[p + 1] : 0.;
+  }
+  __syncwarp();   // every lane holds its inputs: se2 may now be overwritten with finished bands
+#pragma unroll 4
+  for (int t = 1; t < B; t++) {
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      r[m] *= a[m];
+      acc[m] += r[m];
+    }
+    if (lane == 0) se2[t] = acc[0];
+    double in = __shfl_down_sync(0xffffffffu, acc[0], 1);
+    if (lane == 31) in = 0.;
+#pragma unroll
+    for (int m = 0; m < 3; m++) acc[m] = acc[m + 1];
+    acc[3] = in;
+  }
+  __syncwarp();
+}
+
+#if defined(PEAQ_DEV_OLD_LADDER)
+// round-1 ladder (development comparison): one shuffle per band and step
+__device__ void spread_ladder_r1(int B, double* scr, int lane) {
+  const double* sa = scr;
+  const double* se = scr + 128;
+  double* se2 = scr + 256;
   double r[4], a[4], acc[4];
 #pragma unroll
   for (int m = 0; m < 4; m++) {
@@ -247,16 +298,15 @@ __device__ void spread_bands(const DeviceTables* __restrict__ T, int B, double* 
     if (last >= 64) ladder(std::integral_constant<int, 2>(), 0, last < 95 ? last - 63 : 32);
     if (last >= 96) ladder(std::integral_constant<int, 3>(), 0, last - 95);
   }
-  // E2 = E2s^(1/0.4) / norm  (:673-675); x^2.5 = x^2 sqrt(x)
+  __syncwarp();
 #pragma unroll
   for (int m = 0; m < 4; m++) {
     const int i = lane + 32 * m;
-    if (i < B) {
-      const double v = acc[m];
-      out[i] = v * v * sqrt(v) / T->spread_norm[i];
-    }
+    if (i < B) se2[i] = acc[m];
   }
+  __syncwarp();
 }
+#endif
 
 // barrier of the two warps of one stream (ids 1..4), of the four warps of one channel
 // (ids 5, 6) and the arrive/wait pair that guards the ref buffer (ids 7, 8)
@@ -401,7 +451,30 @@ struct FrameMail {
   int bw_test_part[kMaxChannels][2];
   double ehs_x[kMaxChannels][6];
   unsigned long long mbar;
+  // results of the frame that are not band arrays (fused kernel: read by the scan step)
+  double o_ehs[kMaxChannels];
+  double o_snr[2];
+  int o_flags;
+  int o_bw[kMaxChannels][2];
 };
+
+// Shared-memory map of a CTA (doubles): [0, kTwDoubles) twiddles, then one kWorkDoubles buffer per
+// stream (stream = 2 * channel + side), then the FrameMail.
+__device__ __forceinline__ double* frame_stream_buf(double* smem, int stream) {
+  return smem + kTwDoubles + stream * kWorkDoubles;
+}
+__device__ __forceinline__ FrameMail* frame_mail(double* smem, int C) {
+  return reinterpret_cast<FrameMail*>(smem + kTwDoubles + 2 * C * kWorkDoubles);
+}
+// where frame_body<true> leaves the band arrays of channel `chan` (valid until the buffers are reused)
+constexpr int kNoiseOut = 1160;   // test buffer: noise in bands
+__device__ __forceinline__ const double* frame_out_e2(double* smem, int chan, int side) {
+  return side == 0 ? frame_stream_buf(smem, 2 * chan) + kScratchRef + 256
+                   : frame_stream_buf(smem, 2 * chan + 1) + kScratchTest + 256;
+}
+__device__ __forceinline__ const double* frame_out_noise(double* smem, int chan) {
+  return frame_stream_buf(smem, 2 * chan + 1) + kNoiseOut;
+}
 
 __device__ __forceinline__ void chan_sync(int chan) {
   asm volatile("bar.sync %0, 128;" ::"r"(5 + chan) : "memory");
@@ -412,27 +485,55 @@ __device__ __forceinline__ void refbuf_arrive(int chan) {
 __device__ __forceinline__ void refbuf_wait(int chan) {
   asm volatile("bar.sync %0, 128;" ::"r"(7 + chan) : "memory");
 }
+__device__ __forceinline__ void frame_load_twiddles(const DeviceTables* __restrict__ T, double* smem) {
+  double2* tw = reinterpret_cast<double2*>(smem);   // 512 complex
+  for (int i = threadIdx.x; i < 512; i += blockDim.x)
+    tw[i] = make_double2(T->tw1024[i].x, T->tw1024[i].y);
+}
+
+// Whole frame inside both signals and 16-byte aligned: it is staged with two TMA bulk copies
+// (ref -> stream 0's buffer, test -> stream 1's buffer, both unused at that point); otherwise
+// (last, zero-padded frame; odd strides) frame_body fills the same buffers with a guarded copy.
+__device__ __forceinline__ bool frame_tma_ok(const PcmView& pcm, int pair, unsigned frame) {
+  const unsigned long long s0 = (unsigned long long)frame * kFftStep;
+  const float* ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
+  const float* test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  return (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 && (reinterpret_cast<uintptr_t>(test_sig) & 15) == 0 &&
+         s0 + kFftFrame <= pcm.n_samples[pair] && s0 + kFftFrame <= pcm.n_samples_test[pair];
+}
+// one thread: arm the barrier and start both copies (the mbarrier must have been initialised and
+// the two buffers must be free)
+__device__ __forceinline__ void frame_tma_issue(const PcmView& pcm, int pair, unsigned frame, double* smem) {
+  const int C = pcm.channels;
+  FrameMail* mail = frame_mail(smem, C);
+  const unsigned long long s0 = (unsigned long long)frame * kFftStep;
+  const float* ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
+  const float* test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  const unsigned bytes = kFftFrame * C * sizeof(float);
+  mbar_expect_tx(&mail->mbar, 2 * bytes);
+  tma_load_1d(frame_stream_buf(smem, 0), ref_sig + s0 * C, bytes, &mail->mbar);
+  tma_load_1d(frame_stream_buf(smem, 1), test_sig + s0 * C, bytes, &mail->mbar);
+}
 
 // One CTA = one FFT-clock frame of one pair; 4 C warps.  Two warps share a stream (channel c,
 // side: 0 ref, 1 test) up to the weighted power spectrum -- staging, window, FFT, power
 // spectrum, bandwidth -- so every thread holds 16 bins instead of 32 and a CTA needs half the
 // registers per thread: 24 warps per SM instead of 12 for the same shared memory.  After
 // that the four warps of a channel split into tasks:
-//   ref-h0 : grouping + spreading of the ref stream
-//   ref-h1 : grouping + spreading of the test stream
-//   test-h0: half of the ln spectrum ratio and of the noise bands
-//   test-h1: the other halves; then both run the EHS together
-__global__ void __launch_bounds__(256, 3)
-fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned first_frame,
-                  unsigned n_chunk_frames, double* __restrict__ records, RecordLayout L, int B,
-                  int advanced) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+//   ref-h0 : grouping + slopes of the ref stream, then the upward ladder of BOTH streams
+//   ref-h1 : grouping + slopes of the test stream
+//   test-h0/h1: ln spectrum ratio and noise spectrum (one bin per thread), noise in bands,
+//               then both run the EHS together
+// kFused = false: results go to the per-frame record `rec` (global memory);
+// kFused = true : band arrays stay in shared memory (frame_out_e2 / frame_out_noise), scalars in
+//                 the FrameMail; the caller synchronises the CTA before reading them.
+// tma_ok / tma_parity: the caller has issued frame_tma_issue for this frame (phase parity of the
+// mbarrier) -- or not, then the frame is copied here.  The twiddles must be (being) loaded.
+template <bool kFused>
+__device__ __forceinline__ void frame_body(const DeviceTables* __restrict__ T, const PcmView& pcm, int pair,
+                                           unsigned frame, int B, int advanced, double* smem, bool tma_ok,
+                                           unsigned tma_parity, double* __restrict__ rec, const RecordLayout& L) {
   const int C = pcm.channels;
-  const int pair = blockIdx.x / n_chunk_frames;
-  const unsigned chunk_frame = blockIdx.x - pair * n_chunk_frames;
-  const unsigned frame = first_frame + chunk_frame;
-  if (frame >= pcm.n_frames[pair]) return;
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int stream = warp >> 1;       // 2 * channel + side
@@ -440,42 +541,18 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   const int chan = stream >> 1;
   const int side = stream & 1;
   const int t = half * 32 + lane;     // thread within the stream
-  const int role = warp & 3;          // 0 ref-h0, 1 ref-h1, 2 test-h0, 3 test-h1
 
-  double* smem = reinterpret_cast<double*>(smem_raw);
   double2* tw = reinterpret_cast<double2*>(smem);                       // 512 complex
-  double* work = smem + kTwDoubles + stream * kWorkDoubles;
-  FrameMail* mail = reinterpret_cast<FrameMail*>(smem + kTwDoubles + 2 * C * kWorkDoubles);
-
-  for (int i = threadIdx.x; i < 512; i += blockDim.x)
-    tw[i] = make_double2(T->tw1024[i].x, T->tw1024[i].y);
+  double* work = frame_stream_buf(smem, stream);
+  FrameMail* mail = frame_mail(smem, C);
 
   const unsigned long long n_ref = pcm.n_samples[pair], n_test = pcm.n_samples_test[pair];
-  const unsigned long long n_sig = side ? n_test : n_ref;
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
   const float* __restrict__ ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
   const float* __restrict__ test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
-  const float* __restrict__ sig = side ? test_sig : ref_sig;
-  // whole frame inside both signals and 16-byte aligned: stage it with two TMA bulk
-  // copies (ref -> stream 0's buffer, test -> stream 1's buffer, both still unused);
-  // otherwise (last, zero-padded frame; odd strides) a guarded copy fills the same buffers
-  const bool tma_ok = (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(test_sig) & 15) == 0 &&
-                      s0 + kFftFrame <= n_ref && s0 + kFftFrame <= n_test;
-  float* raw_ref = reinterpret_cast<float*>(smem + kTwDoubles);
-  float* raw_test = reinterpret_cast<float*>(smem + kTwDoubles + kWorkDoubles);
-  if (tma_ok) {
-    if (threadIdx.x == 0) mbar_init(&mail->mbar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned bytes = kFftFrame * C * sizeof(float);
-      mbar_expect_tx(&mail->mbar, 2 * bytes);
-      tma_load_1d(raw_ref, ref_sig + s0 * C, bytes, &mail->mbar);
-      tma_load_1d(raw_test, test_sig + s0 * C, bytes, &mail->mbar);
-    }
-  }
-
-  else {
+  float* raw_ref = reinterpret_cast<float*>(frame_stream_buf(smem, 0));
+  float* raw_test = reinterpret_cast<float*>(frame_stream_buf(smem, 1));
+  if (!tma_ok) {
     // guarded copy of the frame (zeros past the end of either signal) into the same buffers
     const unsigned long long base = s0 * (unsigned long long)C;
     for (int i = threadIdx.x; i < kFftFrame * C; i += blockDim.x) {
@@ -488,7 +565,7 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   // ---- phase 1: this thread's 32 samples (complex points n = t + 64 u) into registers ----
   float xs0[16], xs1[16];
   double energy = 0., es = 0., en = 0.;
-  if (tma_ok) mbar_wait(&mail->mbar, 0);
+  if (tma_ok) mbar_wait(&mail->mbar, tma_parity);
   {
     const float* raw = side ? raw_test : raw_ref;
 #pragma unroll
@@ -611,8 +688,6 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     }
   }
 
-  double* rec = records + ((size_t)pair * n_chunk_frames + chunk_frame) * L.stride;
-
   // ---- bandwidth on the register-held spectrum (movs.c:783-803) ----------------------
   if (side == 1) {
     // bins 921..1023: register 8 (bin 1024 - t, t >= 1) and register 9 (bin 960 - t, t <= 39)
@@ -664,8 +739,8 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   if (t == 0) spec[512] = p_mid * T->earw2[512];
   chan_sync(chan);   // both spectra of the channel (and bw_test_part) visible
 
-  double* buf_ref = smem + kTwDoubles + (2 * chan) * kWorkDoubles;
-  double* buf_test = smem + kTwDoubles + (2 * chan + 1) * kWorkDoubles;
+  double* buf_ref = frame_stream_buf(smem, 2 * chan);
+  double* buf_test = frame_stream_buf(smem, 2 * chan + 1);
   const double* spec_ref = buf_ref;
   const double* spec_test = buf_test;
   double* dlog = buf_test + kScratchDlog;
@@ -674,8 +749,21 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
   for (int w = 0; w < 2 * C; w++)
     ehs_valid |= mail->energy[w][0] + mail->energy[w][1] >= 8000. / (32768. * 32768.);
 
+  // Tasks of the channel's four warps: 0, 1: spreading of ref, test; 2, 3: ratio / noise / EHS.
+  // A task is tied to the warp index and with it to one scheduler (SM sub-partition) of the SM:
+  // the six warps a scheduler holds (two per resident CTA) then run the SAME code, which is what
+  // keeps this 140 KB kernel inside the instruction caches (L0 ~6 KB per scheduler, L1.5 32 KB per
+  // SM).  Rotating the tasks with the frame index would spread the FP64 load over the four pipes
+  // but measured 7 % slower: instruction-fetch stalls 8.6 % -> 24.9 % of all warp stall samples.
+#if defined(PEAQ_DEV_ROTATION)
+  const int role = ((warp & 3) + (int)(frame & 3u)) & 3;
+#else
+  const int role = warp & 3;
+#endif
+  const int tk = (role & 1) * 32 + lane;                    // thread within the two-warp task 2 + 3
+  const StreamSync pair_sync{2 + 2 * chan};                 // the test stream's barrier, free since the FFT
   if (role <= 1) {
-    // ---- grouping + internal noise + frequency spreading of one stream ---------------
+    // ---- grouping + internal noise + frequency spreading of one stream ----------------
     const bool skip = role == 1 && advanced;   // the advanced FFT model only needs the ref excitation
     double* scratch = role == 0 ? buf_ref + kScratchRef : buf_test + kScratchTest;
     double* se = scratch + 128;
@@ -687,30 +775,85 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
     refbuf_arrive(chan);   // this warp no longer reads the ref spectrum
     if (!skip) {
       __syncwarp();
-      spread_bands(T, B, scratch, se, scratch + 256, rec + (role * C + chan) * B, lane);
+      spread_prepare(T, B, scratch, se, scratch + 256, lane);
+#if defined(PEAQ_DEV_OLD_LADDER)
+      spread_ladder_r1(B, scratch, lane);
+#else
+      spread_ladder(B, scratch, lane);
+#endif
+      // E2 = E2s^(1/0.4) / norm  (:673-675); x^2.5 = x^2 sqrt(x)
+      const double* fin = scratch + 256;
+      double* out = kFused ? const_cast<double*>(frame_out_e2(smem, chan, role)) : rec + (role * C + chan) * B;
+      for (int i = lane; i < B; i += 32) {
+        const double v = fin[i];
+        out[i] = v * v * sqrt(v) / T->spread_norm[i];
+      }
     }
     if (role == 0 && lane == 0) {
-      int* ints = reinterpret_cast<int*>(rec + L.off_ints);
-      ints[1 + 2 * chan] = bw_ref;
-      ints[2 + 2 * chan] = max(mail->bw_test_part[chan][0], mail->bw_test_part[chan][1]);
+      const int bw_test = max(mail->bw_test_part[chan][0], mail->bw_test_part[chan][1]);
+      if (kFused) {
+        mail->o_bw[chan][0] = bw_ref;
+        mail->o_bw[chan][1] = bw_test;
+      } else {
+        int* ints = reinterpret_cast<int*>(rec + L.off_ints);
+        ints[1 + 2 * chan] = bw_ref;
+        ints[2 + 2 * chan] = bw_test;
+      }
     }
   } else {
-    // ---- ln spectrum ratio (movs.c:1396-1403) and noise in bands (movs.c:988-1000), in halves --
-    const int hh = role - 2;
+    // ---- ln spectrum ratio (movs.c:1396-1403) and noise spectrum (movs.c:993-998), one bin per
+    // thread; then the noise in bands (movs.c:999-1000) ---------------------------------------
+    double* nzs = buf_ref + (kSpecBins - 2);   // nzs[k] = noise bin k, k = 2..768: ref buffer [769, 1536)
+#if defined(PEAQ_DEV_ROLLED)
+#pragma unroll 1
+#else
 #pragma unroll 4
+#endif
     for (int u = 0; u < 8; u++) {
-      const int i = 256 * hh + lane + 32 * u;
+      const int i = tk + 64 * u;
       const double fref = spec_ref[i], ftest = spec_test[i];
-      dlog[i] = (fref == 0. && ftest == 0.) ? 0. : log(ftest / fref);
+      dlog[i] = (fref == 0. && ftest == 0.) ? 0. : peaq_log(ftest / fref);
     }
-    for (int i = 32 * hh + lane; i < B; i += 64)
-      rec[L.off_noise + chan * B + i] = group_band_noise(T, spec_ref, spec_test, i);
+    // Noise in bands, two ways (same arithmetic, same bits).  Basic mode: the spreading warps are
+    // the critical path of the frame and share the FP64 pipes and the shared-memory pipe with
+    // these two, so the noise spectrum is computed where it is consumed, a lane per band, spread
+    // out in time (a burst of 767 square roots at the start of the tail slowed the spreading
+    // warps: 151.8 -> 169.7 ms per 4096 x 10 s).  Advanced mode (55 bands, only the ref stream is
+    // spread): these two warps ARE the critical path, and one bin per thread up front is faster
+    // (157.8 -> 128.7 ms).
+    if (!advanced) {
+      double* out = kFused ? const_cast<double*>(frame_out_noise(smem, chan)) : rec + L.off_noise + chan * B;
+      for (int i = tk; i < B; i += 64) {
+        const int lo = T->band_lo[i], hi = T->band_hi[i];
+        const double wl = T->band_wl[i], wu = T->band_wu[i];
+        double p = 0.;
+        const int n_terms = hi > lo ? hi - lo + 1 : 2;
+#pragma unroll 1
+        for (int j = 0; j < n_terms; j++) {
+          const int k = j == 0 ? lo : (j == 1 ? hi : lo + j - 1);
+          const double w = j == 0 ? wl : (j == 1 ? wu : 1.);
+          const double v = w * noise_bin(spec_ref, spec_test, k);
+          p = j == 0 ? v : p + v;
+        }
+        out[i] = p < 1e-12 ? 1e-12 : p;
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 2 + tk; k < kSpecBins; k += 64) nzs[k] = noise_bin(spec_ref, spec_test, k);
+      __threadfence_block();
+      pair_sync();   // both warps of the task: noise spectrum and ln ratio complete
+      double* out = kFused ? const_cast<double*>(frame_out_noise(smem, chan)) : rec + L.off_noise + chan * B;
+      for (int i = tk; i < B; i += 64) out[i] = group_band_noise(T, nzs, i);
+    }
     __threadfence_block();
-    // both warps: ln ratio complete, ref spectrum dead -- its buffer carries the EHS transforms
+    // both warps: ref spectrum and noise spectrum dead -- the ref buffer carries the EHS transforms
     refbuf_wait(chan);
     double ehs = 0.;
-    if (ehs_valid) ehs = ehs_channel_pair(T, dlog, buf_ref, tw, t, StreamSync{1 + stream}, mail->ehs_x[chan]);
-    if (role == 2 && lane == 0) rec[L.off_ehs + chan] = ehs;
+    if (ehs_valid) ehs = ehs_channel_pair(T, dlog, buf_ref, tw, tk, pair_sync, mail->ehs_x[chan]);
+    if (role == 2 && lane == 0) {
+      if (kFused) mail->o_ehs[chan] = ehs;
+      else rec[L.off_ehs + chan] = ehs;
+    }
   }
 
   if (threadIdx.x == 0) {
@@ -733,32 +876,22 @@ fft_frames_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigned firs
         if (5.f * m >= thr_f * 0.99f) above = replay_threshold_serial(ref_sig, s0, n_ref, c, C);
       }
     }
-    rec[L.off_snr] = sum_s;
-    rec[L.off_snr + 1] = sum_n;
-    int* ints = reinterpret_cast<int*>(rec + L.off_ints);
-    ints[0] = (above ? kRecFlagAbove : 0) | (ehs_valid ? kRecFlagEhsValid : 0);
+    const int flags = (above ? kRecFlagAbove : 0) | (ehs_valid ? kRecFlagEhsValid : 0);
+    if (kFused) {
+      mail->o_snr[0] = sum_s;
+      mail->o_snr[1] = sum_n;
+      mail->o_flags = flags;
+    } else {
+      rec[L.off_snr] = sum_s;
+      rec[L.off_snr + 1] = sum_n;
+      reinterpret_cast<int*>(rec + L.off_ints)[0] = flags;
+    }
   }
 }
 
-}  // namespace
-
-size_t fft_frames_smem_bytes(int channels) {
+constexpr size_t frame_smem_bytes(int channels) {
   return sizeof(double) * (kTwDoubles + 2 * channels * kWorkDoubles) + sizeof(FrameMail);
 }
 
-cudaError_t launch_fft_frames(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
-                              unsigned first_frame, unsigned n_chunk_frames, double* records,
-                              RecordLayout L, int fft_bands, bool advanced, cudaStream_t stream) {
-  if (n_pairs <= 0 || n_chunk_frames == 0) return cudaSuccess;
-  const size_t smem = fft_frames_smem_bytes(pcm.channels);
-  cudaError_t e = cudaFuncSetAttribute(fft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)fft_frames_smem_bytes(kMaxChannels));
-  if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)n_chunk_frames * (unsigned)n_pairs);
-  dim3 block(128 * pcm.channels);
-  fft_frames_kernel<<<grid, block, smem, stream>>>(d_tables, pcm, first_frame, n_chunk_frames, records,
-                                                   L, fft_bands, advanced ? 1 : 0);
-  return cudaGetLastError();
-}
-
+}  // namespace
 }  // namespace peaq

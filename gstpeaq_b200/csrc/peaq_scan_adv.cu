@@ -26,6 +26,7 @@
 // Compiled with -fmad=false (reference rounding); recurrent state is loaded
 // from / stored to global memory at chunk boundaries.
 #include "peaq_engine.h"
+#include "peaq_math.cuh"
 
 #include <climits>
 
@@ -51,10 +52,10 @@ __device__ __forceinline__ double nl_term(double alpha, double thres_fac, double
                                           double ep_test) {
   const double sref = thres_fac * ref_mod + S0;
   const double stest = thres_fac * test_mod + S0;
-  const double beta = exp(-alpha * (ep_test - ep_ref) / ep_ref);
+  const double beta = peaq_exp(-alpha * (ep_test - ep_ref) / ep_ref);
   const double d = stest * ep_test - sref * ep_ref;
-  return exp(0.23 * log(ethres / stest)) *
-         (exp(0.23 * log(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta))) - 1.);
+  return peaq_exp(0.23 * peaq_log(ethres / stest)) *
+         (peaq_exp(0.23 * peaq_log(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta))) - 1.);
 }
 
 // per-band constants of the filter-bank model, staged in shared memory
@@ -117,10 +118,10 @@ fb_spread_kernel(const DeviceTables* __restrict__ T, const double2* __restrict__
 #pragma unroll
       for (int k = 0; k < kFbBands / 2; k++) {
         const int b = part + 2 * k;
-        const double e = sm.slope0[b] + kKappa * log(o[k].x * o[k].x + o[k].y * o[k].y);
+        const double e = sm.slope0[b] + kKappa * peaq_log(o[k].x * o[k].x + o[k].y * o[k].y);
         sm.re[b][t] = o[k].x;
         sm.im[b][t] = o[k].y;
-        sm.cu[b][t] = exp(e < 4 * kLnDist ? e : 4 * kLnDist);
+        sm.cu[b][t] = peaq_exp(e < 4 * kLnDist ? e : 4 * kLnDist);
       }
     }
     __syncthreads();
@@ -277,7 +278,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           // modulation of this stream (modpatt.c:234-250): needs nothing but its own unsmeared
           // excitation, so every warp does its own
           const double a_proc = sm.cst[kCAProc][b];
-          const double loud = exp(0.3 * log(U));
+          const double loud = peaq_exp(0.3 * peaq_log(U));
           const double fd = a_proc * sm.md[chan][side][2][b] +
                             (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][side][0][b]));
           const double fl_ = a_proc * sm.md[chan][side][1][b] + (1. - a_proc) * loud;
@@ -323,8 +324,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           p_den += tf;
           if (loud_frame == UINT_MAX) {   // earmodel.c:890-907
             const double thres = sm.cst[kCThres][b], ethres = sm.cst[kCEthres][b], lfac = sm.cst[kCLoudfac][b];
-            const double a = lfac * (exp(0.23 * log(1. - thres + thres * Er / ethres)) - 1.);
-            const double c2 = lfac * (exp(0.23 * log(1. - thres + thres * Et / ethres)) - 1.);
+            const double a = lfac * (peaq_exp(0.23 * peaq_log(1. - thres + thres * Er / ethres)) - 1.);
+            const double c2 = lfac * (peaq_exp(0.23 * peaq_log(1. - thres + thres * Et / ethres)) - 1.);
             l_r += a > 0. ? a : 0.;
             l_t += c2 > 0. ? c2 : 0.;
           }

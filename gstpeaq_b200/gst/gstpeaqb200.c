@@ -10,11 +10,21 @@
  * evaluation on PAUSED->READY with the console output formats of
  * calculate_di_basic / _advanced / calculate_odg (:1012-1078).
  *
- * GStreamer is not available in the build image, so this file is compile-gated:
+ * GStreamer is not available in the build image, so the real build is gated:
  * `make -C gstpeaq_b200/csrc gst` builds libgstpeaqb200.so when
- * `pkg-config gstreamer-1.0 gstreamer-base-1.0` succeeds.  It has not been
- * exercised here; the tested boundary is the session API itself
- * (tests/test_gpu_parity.py::test_session_*).
+ * `pkg-config gstreamer-1.0` succeeds.  What IS verified here: the file compiles with
+ * -Wall -Wextra -Werror against a stand-in for the GStreamer / GObject API with the real
+ * signatures (tests/gst_stub/), and tests/test_gst_element.py drives the element through that
+ * stand-in like a pipeline would -- caps queries and CAPS events on both pads, buffers of unequal
+ * sizes, EOS aggregation, PAUSED->READY, the properties -- and compares odg / di and the console
+ * output with the reference's known answers.
+ *
+ * Divergences from gstpeaq.c, on purpose:
+ *  - channels are restricted to 1..2 in the pad templates (the engine's kernels are built for
+ *    mono and stereo; the reference takes any count, gstpeaq.c:575-586);
+ *  - a CAPS event that does not change the channel count keeps the model state (the reference
+ *    reallocates it on every CAPS event, gstpeaq.c:575-586); renegotiation mid-stream to the same
+ *    format therefore does not restart the measurement.
  */
 #include <gst/gst.h>
 #include <string.h>
@@ -42,7 +52,7 @@ G_DEFINE_TYPE (GstPeaqB200, gst_peaq_b200, GST_TYPE_ELEMENT)
 enum { PROP_0, PROP_PLAYBACK_LEVEL, PROP_ADVANCED, PROP_DI, PROP_ODG, PROP_TOTALSNR,
   PROP_CONSOLE_OUTPUT, PROP_DEVICE };
 
-#define PEAQ_CAPS "audio/x-raw, format = F32LE, layout = interleaved, rate = (int) 48000"
+#define PEAQ_CAPS "audio/x-raw, format = F32LE, layout = interleaved, rate = (int) 48000, channels = (int) [ 1, 2 ]"
 static GstStaticPadTemplate ref_template =
 GST_STATIC_PAD_TEMPLATE ("ref", GST_PAD_SINK, GST_PAD_ALWAYS, GST_STATIC_CAPS (PEAQ_CAPS));
 static GstStaticPadTemplate test_template =
@@ -57,10 +67,14 @@ ensure_session (GstPeaqB200 * self)
     GST_ELEMENT_ERROR (self, LIBRARY, INIT, ("%s", peaq_b200_last_error ()), (NULL));
     return FALSE;
   }
-  peaq_b200_session_set_playback_level (self->session, self->playback_level);
-  peaq_b200_session_set_advanced (self->session, self->advanced);
-  if (self->channels > 0)
-    peaq_b200_session_set_channels (self->session, self->channels);
+  if (peaq_b200_session_set_playback_level (self->session, self->playback_level) != 0 ||
+      peaq_b200_session_set_advanced (self->session, self->advanced) != 0 ||
+      (self->channels > 0 && peaq_b200_session_set_channels (self->session, self->channels) != 0)) {
+    GST_ELEMENT_ERROR (self, LIBRARY, SETTINGS, ("%s", peaq_b200_last_error ()), (NULL));
+    peaq_b200_session_destroy (self->session);
+    self->session = NULL;
+    return FALSE;
+  }
   return TRUE;
 }
 
@@ -106,16 +120,25 @@ gst_peaq_b200_set_property (GObject * obj, guint id, const GValue * value, GPara
 {
   GstPeaqB200 *self = GST_PEAQ_B200 (obj);
   switch (id) {
-    case PROP_PLAYBACK_LEVEL:
-      self->playback_level = g_value_get_double (value);
-      if (self->session)
-        peaq_b200_session_set_playback_level (self->session, self->playback_level);
+    case PROP_PLAYBACK_LEVEL:{
+      /* takes effect at once on a running measurement, state kept (gstpeaq.c:509-514); the
+       * property only reports a level the engine has accepted */
+      const gdouble level = g_value_get_double (value);
+      if (self->session && peaq_b200_session_set_playback_level (self->session, level) != 0)
+        GST_WARNING_OBJECT (self, "playback_level not changed: %s", peaq_b200_last_error ());
+      else
+        self->playback_level = level;
       break;
-    case PROP_ADVANCED:
-      self->advanced = g_value_get_boolean (value);
-      if (self->session)
-        peaq_b200_session_set_advanced (self->session, self->advanced);
+    }
+    case PROP_ADVANCED:{
+      /* rebuilds the models, like the reference (gstpeaq.c:516-560) */
+      const gboolean advanced = g_value_get_boolean (value);
+      if (self->session && peaq_b200_session_set_advanced (self->session, advanced) != 0)
+        GST_WARNING_OBJECT (self, "advanced not changed: %s", peaq_b200_last_error ());
+      else
+        self->advanced = advanced;
       break;
+    }
     case PROP_CONSOLE_OUTPUT: self->console_output = g_value_get_boolean (value); break;
     case PROP_DEVICE: self->device = g_value_get_int (value); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec);
@@ -170,13 +193,15 @@ gst_peaq_b200_pad_event (GstPad * pad, GstObject * parent, GstEvent * event)
         gint channels = 0;
         gst_structure_get_int (gst_caps_get_structure (caps, 0), "channels", &channels);
         GST_OBJECT_LOCK (self);
+        ret = TRUE;
         if (channels != self->channels) {
-          self->channels = channels;
-          if (self->session)
-            peaq_b200_session_set_channels (self->session, channels);
+          if (self->session && peaq_b200_session_set_channels (self->session, channels) != 0) {
+            GST_WARNING_OBJECT (self, "caps refused: %s", peaq_b200_last_error ());
+            ret = FALSE;
+          } else
+            self->channels = channels;
         }
         GST_OBJECT_UNLOCK (self);
-        ret = TRUE;
       }
       gst_event_unref (event);
       break;

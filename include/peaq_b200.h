@@ -148,7 +148,8 @@ int peaq_b200_session_create(peaq_b200_session **out, int device);
 int peaq_b200_session_destroy(peaq_b200_session *s);
 /* property `advanced` (gstpeaq.c:516-560); resets the per-channel state */
 int peaq_b200_session_set_advanced(peaq_b200_session *s, int advanced);
-/* property `playback_level` (gstpeaq.c:509-514) */
+/* property `playback_level` (gstpeaq.c:509-514): may change at any time; like in the reference the
+ * new level applies from the next frame on and the models' state is kept */
 int peaq_b200_session_set_playback_level(peaq_b200_session *s, double level_db);
 int peaq_b200_session_get_playback_level(const peaq_b200_session *s, double *level_db);
 /* CAPS event -> set_caps (gstpeaq.c:569-593); resets the per-channel state */
@@ -158,8 +159,29 @@ int peaq_b200_session_set_channels(peaq_b200_session *s, int channels);
 int peaq_b200_session_push(peaq_b200_session *s, int pad, const float *interleaved, size_t n);
 /* PAUSED->READY: do_flush + calculate_odg (gstpeaq.c:764-778) */
 int peaq_b200_session_finish(peaq_b200_session *s);
-/* properties odg / di / totalsnr, readable at any time (gstpeaq.c:484-497) */
+/* properties odg / di / totalsnr, readable at any time (gstpeaq.c:484-497).  A push only
+ * QUEUES its work on the GPU (the streaming thread is never stalled, like pad_chain returning
+ * GST_FLOW_OK at once, gstpeaq.c:660); reading a result waits for the pushes queued so far. */
 int peaq_b200_session_get_result(peaq_b200_session *s, peaq_b200_result *out);
+/* Snapshot / restore of a running session: mode, playback level, channels, the samples waiting in
+ * the adapters (gstpeaq.c:116-119), the recurrent state on the device and the last result.  A
+ * restored session continues bit-identically (also on another device of the same kind).
+ * snapshot: *size = bytes needed / written; with buf == NULL only the size is reported. */
+int peaq_b200_session_snapshot(peaq_b200_session *s, void *buf, size_t capacity, size_t *size);
+int peaq_b200_session_restore(peaq_b200_session *s, const void *buf, size_t size);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU batch: pairs are closed computations (all state is per element
+ * instance, gstpeaq.c:110-139), so a batch shards into contiguous blocks of pairs, one engine and
+ * one host thread per device; every device writes its result rows straight into the caller's
+ * array -- that copy is the gather, no device-to-device collective is involved.
+ * devices == NULL / n_devices <= 0: all visible devices.  Host buffers only. */
+typedef struct peaq_b200_multi peaq_b200_multi;
+int peaq_b200_multi_create(peaq_b200_multi **out, const int *devices, int n_devices, int advanced,
+                           double playback_level);
+int peaq_b200_multi_destroy(peaq_b200_multi *m);
+int peaq_b200_multi_device_count(const peaq_b200_multi *m);
+int peaq_b200_multi_run_batch(peaq_b200_multi *m, const peaq_b200_batch *batch, peaq_b200_result *out);
 
 #ifdef __cplusplus
 }

@@ -509,3 +509,226 @@ print(json.dumps({"movs": out["movs"][0][:5].tolist(), "odg": float(out["odg"][0
     np.testing.assert_allclose(a["exc"], b["exc"], rtol=5e-9)
     np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9, atol=1e-12)
     assert abs(a["odg"] - b["odg"]) < 1e-9
+
+
+def _engine_with_env(monkeypatch, advanced=False, **env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    e = G.Engine(0, advanced=advanced)
+    for k in env:
+        monkeypatch.delenv(k)
+    return e
+
+
+@pytest.mark.parametrize("ch", [2, 1])
+def test_fused_persistent_kernel_is_bit_identical_to_two_kernel_path(monkeypatch, ch):
+    """the fused kernel (one persistent CTA per pair, nothing per-frame through HBM) must give
+    the same bits as K1 + records + K2: ragged lengths (incl. empty, sub-frame, exact multiples),
+    leading / trailing silence (INIT / TENTATIVE accumulators), stereo and mono (TMA prefetch on / off)"""
+    lengths = [48000, 30001, 2048, 1, 0, 70000, 4096 + 512, 1023, 2048 + 1024 * 7, 65536]
+    stride = max(lengths) * ch
+    ref = np.zeros((len(lengths) + 1, stride), np.float32)
+    test = np.zeros_like(ref)
+    for p, n in enumerate(lengths):
+        if n:
+            r, t = synth_pair(300 + p, n, ch)
+            ref[p, :n * ch] = r
+            test[p, :n * ch] = t
+    x, y = noise_pair(7, 48765, ch, lead=20000, tail=16000)
+    ref[-1, :x.size] = x
+    test[-1, :y.size] = y
+    ns = np.array(lengths + [48765], np.uint64)
+    fused = _engine_with_env(monkeypatch, PEAQ_B200_FUSED="1")
+    split = _engine_with_env(monkeypatch, PEAQ_B200_FUSED="0")
+    try:
+        a = fused.run_host(ref, test, ch, n_samples=ns)
+        b = split.run_host(ref, test, ch, n_samples=ns)
+        assert fused.last_ms(2) == 0.0 and split.last_ms(2) > 0.0   # really two different paths
+    finally:
+        fused.close()
+        split.close()
+    assert a.tobytes() == b.tobytes()
+    for p, n in enumerate(ns):
+        want = H.oracle_run_pair(ref[p, :int(n) * ch], test[p, :int(n) * ch], ch)
+        check_result(a[p], want, "fused pair %d len %d" % (p, n))
+
+
+def test_threshold_replay_amplitude_sweep(engine):
+    """is_frame_above_threshold (gstpeaq.c:1081-1099): amplitudes around 200/32768 / {5, 1} put
+    frames into the window where K1 cannot decide from the largest |x| and replays the reference's
+    float recurrence literally; flags must equal the oracle's frame by frame"""
+    ch = 1
+    n = 2048 + 1024 * 6
+    thr = 200.0 / 32768.0
+    rng = np.random.default_rng(11)
+    rows_r, rows_t, amps = [], [], []
+    for base in (thr / 5, thr):
+        for f in (0.90, 0.985, 0.995, 0.99999, 0.999999, 1.0, 1.000001, 1.00001, 1.004, 1.009, 1.02, 1.2):
+            amp = np.float32(base * f)
+            sign = np.where(rng.random(n) < 0.5, -1.0, 1.0).astype(np.float32)
+            r = (sign * amp).astype(np.float32)                  # constant magnitude: sliding sums sit at 5 * amp
+            r[::7] *= np.float32(0.5)
+            t = (r * np.float32(0.9)).astype(np.float32)
+            rows_r.append(r)
+            rows_t.append(t)
+            amps.append(float(amp))
+    ref = np.stack(rows_r)
+    test = np.stack(rows_t)
+    engine.keep_records(True)
+    try:
+        out = engine.run_host(ref, test, ch)
+        rec = engine.records(len(amps), G.frames_for_samples(n))
+    finally:
+        engine.keep_records(False)
+    seen = set()
+    for p in range(len(amps)):
+        o = H.OraclePeaq(False, 92.0, ch, fft_trace=16)
+        o.push(ref[p], test[p])
+        o.finish()
+        nf = G.frames_for_samples(n)
+        want = o.fft_trace["above_threshold"][:nf]
+        got = rec["flags"][p, :nf] & 1
+        np.testing.assert_array_equal(got, want, err_msg="amp %g" % amps[p])
+        seen.update(int(v) for v in want)
+        check_result(out[p], o.result(), "amp %g" % amps[p])
+    assert seen == {0, 1}   # the sweep really crosses the threshold
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_bench_shaped_batch_matches_oracle(advanced):
+    """the bench workload's shape -- 10 s synthetic stereo pairs, one batch call -- against the oracle
+    (24 pairs basic, 8 advanced: the oracle's filter bank runs ~0.7 s per 10 s pair)"""
+    ch, ns = 2, 480000
+    n_pairs = 8 if advanced else 24
+    ref, test = G.synth_pairs_host(2000, n_pairs, ns, ch)
+    e = G.Engine(0, advanced=advanced)
+    try:
+        out = e.run_host(ref, test, ch)
+    finally:
+        e.close()
+    for p in range(n_pairs):
+        want = H.oracle_run_pair(ref[p], test[p], ch, advanced=advanced)
+        check_result(out[p], want, "pair %d" % p)
+
+
+def _stream(p, ref, test, ch, lo, hi, step):
+    for a in range(lo, hi, step):
+        b = min(a + step, hi)
+        p.chain_ref(ref[a * ch:b * ch])
+        p.chain_test(test[a * ch:b * ch])
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_session_snapshot_restore_continues_bit_identically(advanced):
+    """a snapshot taken mid-stream (samples waiting in the adapters + recurrent
+    state on the device) restored into ANOTHER session continues to the same bits as the
+    uninterrupted session; the snapshotted session itself is not disturbed either"""
+    ch, n = 2, 70000
+    ref, test = synth_pair(77, n, ch)
+    cut = 33333                       # not a multiple of any frame size: both adapters hold samples
+    whole = G.Peaq(0, advanced=advanced, console_output=False)
+    whole.set_caps(ch)
+    _stream(whole, ref, test, ch, 0, n, 5000)
+    want = whole.stop()
+    whole.close()
+
+    a = G.Peaq(0, advanced=advanced, console_output=False)
+    a.set_caps(ch)
+    _stream(a, ref, test, ch, 0, cut, 5000)
+    blob = a.snapshot()
+    assert len(blob) > 1000
+    b = G.Peaq(0, console_output=False)          # mode, level and channels come from the snapshot
+    b.restore(blob)
+    assert b.advanced == advanced
+    _stream(b, ref, test, ch, cut, n, 7000)
+    got_b = b.stop()
+    _stream(a, ref, test, ch, cut, n, 3000)      # the original continues as well
+    got_a = a.stop()
+    a.close()
+    b.close()
+    for got in (got_a, got_b):
+        for k in ("odg", "di", "totalsnr", "frames_fft", "frames_fb", "loudness_reached_frame"):
+            assert got[k] == want[k] or (math.isnan(got[k]) and math.isnan(want[k])), k
+        np.testing.assert_array_equal(got["movs"], want["movs"])
+    with pytest.raises(G.PeaqError):
+        b2 = G.Peaq(0, console_output=False)
+        try:
+            b2.restore(blob[:100])
+        finally:
+            b2.close()
+
+
+def test_session_pushes_do_not_wait_for_the_gpu():
+    """pad_chain returns at once (gstpeaq.c:660); here a push only queues copies and kernels --
+    results are bit-identical to a session that reads the result after every push (= synchronises)"""
+    ch, n = 2, 120000
+    ref, test = synth_pair(5, n, ch)
+    res = []
+    for read_every_push in (False, True):
+        p = G.Peaq(0, console_output=False)
+        p.set_caps(ch)
+        for a in range(0, n, 1500):              # 80 pushes per pad: more than the 64 the session lets queue up
+            p.chain_ref(ref[a * ch:(a + 1500) * ch])
+            p.chain_test(test[a * ch:(a + 1500) * ch])
+            if read_every_push:
+                p.odg
+        res.append(p.stop())
+        p.close()
+    assert res[0]["odg"] == res[1]["odg"] and res[0]["di"] == res[1]["di"]
+    np.testing.assert_array_equal(res[0]["movs"], res[1]["movs"])
+    want = H.oracle_run_pair(ref, test, ch)
+    assert abs(res[0]["odg"] - want["odg"]) < ODG_ATOL
+
+
+def test_session_playback_level_can_change_mid_stream():
+    """property `playback_level` is writable at any time and keeps the model state (gstpeaq.c:509-514)"""
+    ch, n = 1, 60000
+    ref, test = synth_pair(8, n, ch)
+
+    def run(levels):
+        p = G.Peaq(0, console_output=False, playback_level=levels[0])
+        p.set_caps(ch)
+        _stream(p, ref, test, ch, 0, n // 2, 4000)
+        p.playback_level = levels[1]
+        assert p.playback_level == levels[1]
+        _stream(p, ref, test, ch, n // 2, n, 4000)
+        r = p.stop()
+        p.close()
+        return r
+
+    same = run((92.0, 92.0))
+    want = H.oracle_run_pair(ref, test, ch)
+    assert abs(same["odg"] - want["odg"]) < ODG_ATOL and same["frames_fft"] == want["frames_fft"]
+    mixed, low = run((92.0, 70.0)), run((70.0, 70.0))
+    assert same["frames_fft"] == mixed["frames_fft"] == low["frames_fft"]     # no restart of the stream
+    assert math.isfinite(mixed["odg"]) and mixed["odg"] != same["odg"] and mixed["odg"] != low["odg"]
+
+
+def test_multi_engine_shards_a_batch_over_devices():
+    """peaq_b200_multi: contiguous blocks of pairs per device, rows gathered into one host array;
+    with one GPU in the box both engines sit on device 0, which exercises the same host logic"""
+    ch = 2
+    lengths = [48000, 30001, 2048, 70000, 1023, 0, 5000]
+    stride = max(lengths) * ch
+    ref = np.zeros((len(lengths), stride), np.float32)
+    test = np.zeros_like(ref)
+    for p, n in enumerate(lengths):
+        if n:
+            r, t = synth_pair(500 + p, n, ch)
+            ref[p, :n * ch] = r
+            test[p, :n * ch] = t
+    ns = np.array(lengths, np.uint64)
+    n_dev = G.device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    m = G.MultiEngine(devices)
+    e = G.Engine(0)
+    try:
+        assert m.device_count() == len(devices)
+        a = m.run_host(ref, test, ch, n_samples=ns)
+        b = e.run_host(ref, test, ch, n_samples=ns)
+        one = m.run_host(ref[:1], test[:1], ch, n_samples=ns[:1])     # fewer pairs than devices
+    finally:
+        m.close()
+        e.close()
+    assert a.tobytes() == b.tobytes()
+    assert one.tobytes() == b[:1].tobytes()
