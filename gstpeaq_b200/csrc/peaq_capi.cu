@@ -177,6 +177,9 @@ struct Engine {
   size_t record_budget_bytes = (size_t)16 << 30;
   int sm_count = 148;
   int fused_mode = 0;    // PEAQ_B200_FUSED=1: the fused persistent kernel for basic-mode batches
+  int pipeline_mode = -1;   // PEAQ_B200_PIPELINE: 1 always, 0 never, default: batches of few pairs
+  cudaStream_t scan_stream = nullptr;
+  cudaEvent_t ev_rec_ready[2] = {nullptr, nullptr}, ev_rec_free[2] = {nullptr, nullptr};
 
   int init() {
     PEAQ_CUDA(cudaSetDevice(device));
@@ -200,6 +203,7 @@ struct Engine {
     PEAQ_CUDA(cudaMemcpy(d_tables, h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice));
     PEAQ_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     if (const char* env = std::getenv("PEAQ_B200_FUSED")) fused_mode = std::atoi(env) ? 1 : 0;
+    if (const char* env = std::getenv("PEAQ_B200_PIPELINE")) pipeline_mode = std::atoi(env) ? 1 : 0;
     if (const char* env = std::getenv("PEAQ_B200_RECORD_BUDGET_MB")) {
       const long mb = std::atol(env);
       if (mb > 0) record_budget_bytes = (size_t)mb << 20;
@@ -230,6 +234,14 @@ struct Engine {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     if (hp_stream) cudaStreamSynchronize(hp_stream);
+    if (scan_stream) {
+      cudaStreamSynchronize(scan_stream);
+      for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(ev_rec_ready[i]);
+        cudaEventDestroy(ev_rec_free[i]);
+      }
+      cudaStreamDestroy(scan_stream);
+    }
     for (auto& e : events) {
       cudaEventDestroy(e.a);
       cudaEventDestroy(e.b);
@@ -260,7 +272,7 @@ struct Engine {
     delete h_tables;
   }
 
-  int timer_begin(int which) {
+  int timer_begin(int which, cudaStream_t on = nullptr) {
     if (events_used == events.size()) {
       EventPair p;
       p.which = which;
@@ -269,11 +281,11 @@ struct Engine {
       events.push_back(p);
     }
     events[events_used].which = which;
-    PEAQ_CUDA(cudaEventRecord(events[events_used].a, stream));
+    PEAQ_CUDA(cudaEventRecord(events[events_used].a, on ? on : stream));
     return 0;
   }
-  int timer_end() {
-    PEAQ_CUDA(cudaEventRecord(events[events_used].b, stream));
+  int timer_end(cudaStream_t on = nullptr) {
+    PEAQ_CUDA(cudaEventRecord(events[events_used].b, on ? on : stream));
     events_used++;
     return 0;
   }
@@ -402,6 +414,61 @@ struct Engine {
     return 0;
   }
 
+  // Basic mode, few pairs (long items): K2 runs one CTA per pair and is bound by the latency of its
+  // frame step, K1 is frame-parallel.  The FFT clock is cut into chunks of frames and K2 of chunk
+  // i (scan stream, high priority: a handful of CTAs) runs underneath K1 of chunk i + 1 (main
+  // stream, fills the rest of the GPU); records are double-buffered.  Same kernels, same chunked
+  // state hand-over as the serial loop: bit-identical results.
+  int run_fft_clock_pipelined(const PcmView& pcm, int n_pairs, unsigned max_frames, const RecordLayout& L,
+                              const StateLayout& S, PairResult* d_res) {
+    const int B = h_tables->fft_bands;
+    const size_t rec_bytes = (size_t)L.stride * sizeof(double);
+    // >= 8 chunks so that the first K1 and the last K2 (which nothing hides) stay small, chunks of
+    // at least 64 frames, two buffers within the record budget
+    size_t chunk = std::max<size_t>((max_frames + 11) / 12, 64);
+    const size_t fit = record_budget_bytes / (2 * (size_t)n_pairs * rec_bytes);
+    chunk = std::max<size_t>(std::min(chunk, std::max<size_t>(fit, 1)), 1);
+    const size_t buf_doubles = (size_t)n_pairs * chunk * L.stride;
+    int rc = ensure(&d_records, &records_cap, 2 * buf_doubles);
+    if (rc) return rc;
+    if (!scan_stream) {
+      int prio_lo = 0, prio_hi = 0;
+      PEAQ_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      PEAQ_CUDA(cudaStreamCreateWithPriority(&scan_stream, cudaStreamNonBlocking, prio_hi));
+      for (int i = 0; i < 2; i++) {
+        PEAQ_CUDA(cudaEventCreateWithFlags(&ev_rec_ready[i], cudaEventDisableTiming));
+        PEAQ_CUDA(cudaEventCreateWithFlags(&ev_rec_free[i], cudaEventDisableTiming));
+      }
+    }
+    // everything queued so far on the main stream (plans, state init) precedes the first scan
+    PEAQ_CUDA(cudaEventRecord(ev_rec_free[0], stream));
+    PEAQ_CUDA(cudaStreamWaitEvent(scan_stream, ev_rec_free[0], 0));
+    unsigned first = 0;
+    for (int i = 0; first < max_frames; i++) {
+      const unsigned n = (unsigned)std::min<size_t>(chunk, max_frames - first);
+      const int buf = i & 1;
+      double* rec = d_records + (size_t)buf * buf_doubles;
+      if (i >= 2) PEAQ_CUDA(cudaStreamWaitEvent(stream, ev_rec_free[buf], 0));   // K2 of chunk i - 2 has read it
+      if ((rc = timer_begin(1))) return rc;
+      PEAQ_CUDA(launch_fft_frames(d_tables, pcm, n_pairs, first, n, rec, L, B, advanced, stream));
+      if ((rc = timer_end())) return rc;
+      PEAQ_CUDA(cudaEventRecord(ev_rec_ready[buf], stream));
+      PEAQ_CUDA(cudaStreamWaitEvent(scan_stream, ev_rec_ready[buf], 0));
+      if ((rc = timer_begin(2, scan_stream))) return rc;
+      PEAQ_CUDA(launch_scan_basic(d_tables, rec, L, pcm.n_frames, first, n, d_state, S, d_res, n_pairs, scan_stream));
+      if ((rc = timer_end(scan_stream))) return rc;
+      PEAQ_CUDA(cudaEventRecord(ev_rec_free[buf], scan_stream));
+      launches += 2;
+      first += n;
+    }
+    // join: the main stream continues (result copy, next batch) after the last scan
+    PEAQ_CUDA(cudaEventRecord(ev_rec_ready[0], scan_stream));
+    PEAQ_CUDA(cudaStreamWaitEvent(stream, ev_rec_ready[0], 0));
+    last_layout = L;
+    last_records_doubles = 0;
+    return 0;
+  }
+
   // Runs the frames described by the plan(s) for `n_pairs` pairs whose PCM is
   // resident on the device, reading from sample 0 of the given buffers.
   // reset_state: start from fresh state (else continue a session).
@@ -451,6 +518,9 @@ struct Engine {
         if ((rc = timer_end())) return rc;
         last_layout = L;
         last_records_doubles = 0;
+      } else if (!keep_records && max_frames >= 256 &&
+                 (pipeline_mode == 1 || (pipeline_mode < 0 && n_pairs < 2 * sm_count))) {
+        if ((rc = run_fft_clock_pipelined(pcm, n_pairs, max_frames, L, S, d_res))) return rc;
       } else {
         rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first, unsigned n) {
           return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_res,
@@ -619,6 +689,7 @@ struct BatchCleanup {
     if (ok) return;
     cudaStreamSynchronize(e->stream);
     cudaStreamSynchronize(e->copy_stream);
+    if (e->scan_stream) cudaStreamSynchronize(e->scan_stream);
     e->events_used = 0;
     e->plan_hold_ns.clear();
     e->plan_hold_nf.clear();

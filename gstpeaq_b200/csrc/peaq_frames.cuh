@@ -160,12 +160,13 @@ __device__ __forceinline__ double group_band_noise(const DeviceTables* __restric
 __device__ void spread_prepare(const DeviceTables* __restrict__ T, int B, double* sa, double* se,
                                double* se2, int lane) {
   const double dz02 = 0.2 * T->dz;
-  // four bands per lane
-#if defined(PEAQ_DEV_ROLLED)
+  // Four bands per lane, one after the other: unrolling this loop (24 inlined ln / exp) and the
+  // ratio loop below bought nothing -- the frame kernel is not bound by a warp's own instruction
+  // latency but by the instruction caches and the shared-memory pipe of the SM --
+  // and cost 1500 instructions of code (149.7 -> 146.3 ms per 4096 x 10 s rolled).  For the same
+  // reason the branch-free division / square root / ln / exp of peaq_math.cuh, which speed the
+  // latency-bound scan kernels up by 18 %, are NOT used here: measured 149.7 -> 164.1 ms.
 #pragma unroll 1
-#else
-#pragma unroll
-#endif
   for (int m = 0; m < 4; m++) {
     const int i = lane + 32 * m;
     const int ii = i < B ? i : B - 1;
@@ -804,11 +805,7 @@ __device__ __forceinline__ void frame_body(const DeviceTables* __restrict__ T, c
     // ---- ln spectrum ratio (movs.c:1396-1403) and noise spectrum (movs.c:993-998), one bin per
     // thread; then the noise in bands (movs.c:999-1000) ---------------------------------------
     double* nzs = buf_ref + (kSpecBins - 2);   // nzs[k] = noise bin k, k = 2..768: ref buffer [769, 1536)
-#if defined(PEAQ_DEV_ROLLED)
 #pragma unroll 1
-#else
-#pragma unroll 4
-#endif
     for (int u = 0; u < 8; u++) {
       const int i = tk + 64 * u;
       const double fref = spec_ref[i], ftest = spec_test[i];

@@ -299,16 +299,16 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
 
   // modulation (modpatt.c:234-250): needs nothing but the unsmeared excitations, so it sits in
   // this phase, where its exp/log chain overlaps the detection-probability chain below
-  const double Lr = peaq_exp(0.3 * peaq_log(E2r)), Lt = peaq_exp(0.3 * peaq_log(E2t));
+  const double Lr = peaq_exp_clamped(0.3 * peaq_log_pos(E2r)), Lt = peaq_exp_clamped(0.3 * peaq_log_pos(E2t));
   const double fd_r = a_proc * st.get(10) + (1 - a_proc) * (deriv_factor * fabs(Lr - st.get(8)));
   const double fl_r = a_proc * st.get(9) + (1. - a_proc) * Lr;
-  const double mod_r = fd_r / (1. + fl_r / 0.3);
+  const double mod_r = peaq_div(fd_r, 1. + peaq_div(fl_r, 0.3));
   st.set(10, fd_r);
   st.set(9, fl_r);
   st.set(8, Lr);
   const double fd_t = a_proc * st.get(13) + (1 - a_proc) * (deriv_factor * fabs(Lt - st.get(11)));
   const double fl_t = a_proc * st.get(12) + (1. - a_proc) * Lt;
-  const double mod_t = fd_t / (1. + fl_t / 0.3);
+  const double mod_t = peaq_div(fd_t, 1. + peaq_div(fl_t, 0.3));
   st.set(13, fd_t);
   st.set(12, fl_t);
   st.set(11, Lt);
@@ -320,15 +320,15 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   double r2[kRed2];
   {
     const double diff = fabs(mod_r - mod_t);
-    r2[0] = diff / (1. + mod_r);
+    r2[0] = peaq_div(diff, 1. + mod_r);
     const double w = mod_t >= mod_r ? 1. : .1;
-    r2[1] = w * diff / (0.01 + mod_r);
-    r2[2] = fl_r / (fl_r + 100. * kc.in03());
+    r2[1] = peaq_div(w * diff, 0.01 + mod_r);
+    r2[2] = peaq_div(fl_r, fl_r + 100. * kc.in03());
   }
   const double sref = 0.15 * mod_r + 0.5;
   const double stest = 0.15 * mod_t + 0.5;
-  const double nl_fac = peaq_exp(0.23 * peaq_log(kc.in_noise() / stest));
-  const double curr_nmr = nz / (Er / kc.maskdiff());
+  const double nl_fac = peaq_exp_clamped(0.23 * peaq_log_pos(peaq_div(kc.in_noise(), stest)));
+  const double curr_nmr = peaq_div(nz, peaq_div(Er, kc.maskdiff()));
   r2[4] = curr_nmr;
   double nmr_max = curr_nmr > 0. ? curr_nmr : 0.;
 
@@ -338,33 +338,33 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   st.set(2, Rf);
   st.set(3, Tf);
   double r1[kRed1];
-  r1[0] = active ? sqrt(Rf * Tf) : 0.;
+  r1[0] = active ? peaq_sqrt(Rf * Tf) : 0.;
   r1[1] = active ? Tf : 0.;
   // loudness until the latch is set (earmodel.c:890-907)
   r1[2] = 0.;
   r1[3] = 0.;
   if (loud_frame == UINT_MAX && active) {
     const double loudfac = kc.loudfac(), thres = kc.thres(), ethres = kc.ethres();
-    const double lr = loudfac * (peaq_exp(0.23 * peaq_log(1. - thres + thres * Er / ethres)) - 1.);
-    const double lt = loudfac * (peaq_exp(0.23 * peaq_log(1. - thres + thres * Et / ethres)) - 1.);
+    const double lr = loudfac * (peaq_exp_clamped(0.23 * peaq_log_pos(1. - thres + peaq_div(thres * Er, ethres))) - 1.);
+    const double lt = loudfac * (peaq_exp_clamped(0.23 * peaq_log_pos(1. - thres + peaq_div(thres * Et, ethres))) - 1.);
     r1[2] = lr > 0. ? lr : 0.;
     r1[3] = lt > 0. ? lt : 0.;
   }
   // detection probability of this channel (movs.c:1240-1260)
   {
-    const double eref_db = 10. * peaq_log10(Er);
-    const double etest_db = 10. * peaq_log10(Et);
+    const double eref_db = 10. * (peaq_log_pos(Er) * 0.4342944819032518);
+    const double etest_db = 10. * (peaq_log_pos(Et) * 0.4342944819032518);
     const double l = 0.3 * (eref_db > etest_db ? eref_db : etest_db) + 0.7 * etest_db;
     const double l2 = l * l;
-    const double s = l > 0. ? 5.95072 * peaq_exp(1.71332 * peaq_log(6.39468 / l)) + 9.01033e-11 * (l2 * l2) +
+    const double s = l > 0. ? 5.95072 * peaq_exp_clamped(1.71332 * peaq_log_pos(peaq_div(6.39468, l))) + 9.01033e-11 * (l2 * l2) +
                                   5.05622e-6 * (l2 * l) - 0.00102438 * l * l + 0.0550197 * l -
                                   0.198719
                             : 1e30;
     const double e = eref_db - etest_db;
-    const double t1 = e / s, t2 = t1 * t1;
+    const double t1 = peaq_div(e, s), t2 = t1 * t1;
     const double tb = eref_db > etest_db ? t2 * t2 : t2 * t2 * t2;   // (e/s)^b, b = 4 or 6
-    pq[c][0][b] = 1. - peaq_exp(-0.6931471805599453 * tb);   // 1 - 0.5^tb
-    pq[c][1][b] = fabs(trunc(e)) / s;
+    pq[c][0][b] = 1. - peaq_exp_clamped(-0.6931471805599453 * tb);   // 1 - 0.5^tb
+    pq[c][1][b] = peaq_div(fabs(trunc(e)), s);
   }
 #pragma unroll
   for (int k = 0; k < kRed1; k++) {
@@ -378,11 +378,11 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
     tot1[k] = ((red1[par][c][0][k] + red1[par][c][1][k]) + red1[par][c][2][k]) + red1[par][c][3][k];
 
   // level adaptation, second part (leveladapter.c:278-308)
-  const double lev_corr = tot1[0] * tot1[0] / (tot1[1] * tot1[1]);
+  const double lev_corr = peaq_div(tot1[0] * tot1[0], tot1[1] * tot1[1]);
   double lcr, lct;
   if (lev_corr > 1) {
     lct = Et;
-    lcr = Er / lev_corr;
+    lcr = peaq_div(Er, lev_corr);
   } else {
     lcr = Er;
     lct = Et * lev_corr;
@@ -394,9 +394,9 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   double pa_r, pa_t;
   if (fnum >= fden) {
     pa_r = 1.;
-    pa_t = fden / fnum;
+    pa_t = peaq_div(fden, fnum);
   } else {
-    pa_r = fnum / fden;
+    pa_r = peaq_div(fnum, fden);
     pa_t = 1.;
   }
   pa[c][0][b] = pa_r;
@@ -415,8 +415,8 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
     ra_r += pa[c][0][l];
     ra_t += pa[c][1][l];
   }
-  ra_r /= (m1 + m2 + 1);
-  ra_t /= (m1 + m2 + 1);
+  ra_r = peaq_div(ra_r, (double)(m1 + m2 + 1));
+  ra_t = peaq_div(ra_t, (double)(m1 + m2 + 1));
   const double pcr = a_proc * st.get(6) + (1 - a_proc) * ra_r;
   const double pct = a_proc * st.get(7) + (1 - a_proc) * ra_t;
   st.set(6, pcr);
@@ -426,9 +426,9 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   // noise loudness term (movs.c:725-738) with alpha 1.5, ThresFac 0.15, S0 0.5; the factor
   // that only depends on the test modulation was prepared in front of barrier A
   {
-    const double beta = peaq_exp(-1.5 * (adt - adr) / adr);
+    const double beta = peaq_exp_clamped(peaq_div(-1.5 * (adt - adr), adr));
     const double d = stest * adt - sref * adr;
-    r2[3] = nl_fac * (peaq_exp(0.23 * peaq_log(1. + (d > 0. ? d : 0.) / (kc.in_noise() + sref * adr * beta))) - 1.);
+    r2[3] = nl_fac * (peaq_exp_clamped(0.23 * peaq_log_pos(1. + peaq_div(d > 0. ? d : 0., kc.in_noise() + sref * adr * beta))) - 1.);
   }
   // binaural detection (movs.c:1261-1267), evaluated by channel 0's threads
   double one_minus_p = 1., qsteps = 0.;

@@ -52,10 +52,10 @@ __device__ __forceinline__ double nl_term(double alpha, double thres_fac, double
                                           double ep_test) {
   const double sref = thres_fac * ref_mod + S0;
   const double stest = thres_fac * test_mod + S0;
-  const double beta = peaq_exp(-alpha * (ep_test - ep_ref) / ep_ref);
+  const double beta = peaq_exp_clamped(peaq_div(-alpha * (ep_test - ep_ref), ep_ref));
   const double d = stest * ep_test - sref * ep_ref;
-  return peaq_exp(0.23 * peaq_log(ethres / stest)) *
-         (peaq_exp(0.23 * peaq_log(1. + (d > 0. ? d : 0.) / (ethres + sref * ep_ref * beta))) - 1.);
+  return peaq_exp_clamped(0.23 * peaq_log_pos(peaq_div(ethres, stest))) *
+         (peaq_exp_clamped(0.23 * peaq_log_pos(1. + peaq_div(d > 0. ? d : 0., ethres + sref * ep_ref * beta))) - 1.);
 }
 
 // per-band constants of the filter-bank model, staged in shared memory
@@ -278,14 +278,14 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           // modulation of this stream (modpatt.c:234-250): needs nothing but its own unsmeared
           // excitation, so every warp does its own
           const double a_proc = sm.cst[kCAProc][b];
-          const double loud = peaq_exp(0.3 * peaq_log(U));
+          const double loud = peaq_exp_clamped(0.3 * peaq_log_pos(U));
           const double fd = a_proc * sm.md[chan][side][2][b] +
                             (1 - a_proc) * (deriv_factor * fabs(loud - sm.md[chan][side][0][b]));
           const double fl_ = a_proc * sm.md[chan][side][1][b] + (1. - a_proc) * loud;
           sm.md[chan][side][2][b] = fd;
           sm.md[chan][side][1][b] = fl_;
           sm.md[chan][side][0][b] = loud;
-          mod_own[sl] = fd / (1. + fl_ / 0.3);
+          mod_own[sl] = peaq_div(fd, 1. + peaq_div(fl_, 0.3));
           avl_own[sl] = fl_;
           sm.mod[warp][b] = mod_own[sl];
         }
@@ -320,12 +320,12 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           const double tf = a_proc * sm.lv[chan][1][b] + (1 - a_proc) * Et;
           sm.lv[chan][0][b] = rf;
           sm.lv[chan][1][b] = tf;
-          p_num += sqrt(rf * tf);
+          p_num += peaq_sqrt(rf * tf);
           p_den += tf;
           if (loud_frame == UINT_MAX) {   // earmodel.c:890-907
             const double thres = sm.cst[kCThres][b], ethres = sm.cst[kCEthres][b], lfac = sm.cst[kCLoudfac][b];
-            const double a = lfac * (peaq_exp(0.23 * peaq_log(1. - thres + thres * Er / ethres)) - 1.);
-            const double c2 = lfac * (peaq_exp(0.23 * peaq_log(1. - thres + thres * Et / ethres)) - 1.);
+            const double a = lfac * (peaq_exp_clamped(0.23 * peaq_log_pos(1. - thres + peaq_div(thres * Er, ethres))) - 1.);
+            const double c2 = lfac * (peaq_exp_clamped(0.23 * peaq_log_pos(1. - thres + peaq_div(thres * Et, ethres))) - 1.);
             l_r += a > 0. ? a : 0.;
             l_t += c2 > 0. ? c2 : 0.;
           }
@@ -338,7 +338,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
         l_t = warp_sum(l_t) * (24. / kFbBands);
         if (lane == 0 && l_r > 0.1 && l_t > 0.1) sm.latch = 1;   // gstpeaq.c:841-845
       }
-      const double lev_corr = p_num * p_num / (p_den * p_den);
+      const double lev_corr = peaq_div(p_num * p_num, p_den * p_den);
 #pragma unroll
       for (int sl = 0; sl < 2; sl++) {
         const int b = lane + 32 * sl;
@@ -348,7 +348,7 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           const double Er = sm.ex_e[2 * chan][b], Et = sm.ex_e[2 * chan + 1][b];
           if (lev_corr > 1) {
             lct[sl] = Et;
-            lcr[sl] = Er / lev_corr;
+            lcr[sl] = peaq_div(Er, lev_corr);
           } else {
             lcr[sl] = Er;
             lct[sl] = Et * lev_corr;
@@ -359,9 +359,9 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           sm.lv[chan][3][b] = den;
           if (num >= den) {
             sm.pa[chan][0][b] = 1.;
-            sm.pa[chan][1][b] = den / num;
+            sm.pa[chan][1][b] = peaq_div(den, num);
           } else {
-            sm.pa[chan][0][b] = num / den;
+            sm.pa[chan][0][b] = peaq_div(num, den);
             sm.pa[chan][1][b] = 1.;
           }
         }
@@ -410,8 +410,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
           const double mod_r = mod_own[sl], mod_t = sm.mod[warp + 1][b];
           if (md_gate) {   // movs.c:226-242 with levWt = 1 (no second accumulator)
             const double diff = fabs(mod_r - mod_t);
-            s_md += diff / (1. + mod_r);
-            s_wt += avl_own[sl] / (avl_own[sl] + 1. * sm.cst[kCNoise03][b]);
+            s_md += peaq_div(diff, 1. + mod_r);
+            s_wt += peaq_div(avl_own[sl], avl_own[sl] + 1. * sm.cst[kCNoise03][b]);
           }
           if (nl_gate)   // peaq_mov_noise_loud_asym, first term (movs.c:551-577)
             s_nl += nl_term(2.5, 0.3, 1., sm.cst[kCNoise][b], mod_r, mod_t, adr[sl], adt[sl]);

@@ -732,3 +732,31 @@ def test_multi_engine_shards_a_batch_over_devices():
         e.close()
     assert a.tobytes() == b.tobytes()
     assert one.tobytes() == b[:1].tobytes()
+
+
+def test_pipelined_chunks_are_bit_identical_to_the_serial_loop(monkeypatch):
+    """few-pair batches run K2 of chunk i underneath K1 of chunk i + 1 on a second stream
+    (double-buffered records): same bits as the serial K1 -> K2 loop, ragged lengths included"""
+    ch = 2
+    lengths = [400000, 262144 + 2048, 300001, 1000, 0, 350000]
+    stride = max(lengths) * ch
+    ref = np.zeros((len(lengths), stride), np.float32)
+    test = np.zeros_like(ref)
+    for p, n in enumerate(lengths):
+        if n:
+            r, t = synth_pair(700 + p, n, ch)
+            ref[p, :n * ch] = r
+            test[p, :n * ch] = t
+    ns = np.array(lengths, np.uint64)
+    piped = _engine_with_env(monkeypatch, PEAQ_B200_PIPELINE="1", PEAQ_B200_RECORD_BUDGET_MB="8")
+    serial = _engine_with_env(monkeypatch, PEAQ_B200_PIPELINE="0")
+    try:
+        a = piped.run_host(ref, test, ch, n_samples=ns)
+        a2 = piped.run_host(ref, test, ch, n_samples=ns)     # and again: events / buffers are reusable
+        b = serial.run_host(ref, test, ch, n_samples=ns)
+    finally:
+        piped.close()
+        serial.close()
+    assert a.tobytes() == b.tobytes() and a2.tobytes() == b.tobytes()
+    want = H.oracle_run_pair(ref[2, :lengths[2] * ch], test[2, :lengths[2] * ch], ch)
+    check_result(a[2], want, "pipelined pair 2")
