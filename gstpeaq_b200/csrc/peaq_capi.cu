@@ -177,6 +177,7 @@ struct Engine {
   size_t record_budget_bytes = (size_t)16 << 30;
   int sm_count = 148;
   int fused_mode = 0;    // PEAQ_B200_FUSED=1: the fused persistent kernel for basic-mode batches
+  unsigned long long fb_pos = 0;   // filter-bank clock: samples consumed so far by the running item (session)
   int pipeline_mode = -1;   // PEAQ_B200_PIPELINE: 1 always, 0 never, default: batches of few pairs
   cudaStream_t scan_stream = nullptr;
   cudaEvent_t ev_rec_ready[2] = {nullptr, nullptr}, ev_rec_free[2] = {nullptr, nullptr};
@@ -556,11 +557,26 @@ struct Engine {
       const size_t rec_bytes_all = (size_t)n_pairs * std::max<unsigned>(max_frames, 1) * L.stride * sizeof(double);
       // (beyond ~2 scan CTAs per SM the scan starts to displace frame-kernel CTAs and the
       // overlap stops paying: 4096 pairs measured 878 ms against 870 ms without it)
-      const bool whole = reset_state && !keep_records && max_fb_frames > 0 && d_ref_fb == nullptr &&
+      bool whole = reset_state && !keep_records && max_fb_frames > 0 && d_ref_fb == nullptr &&
                          n_streams <= 8192 &&
                          (size_t)n_streams * (kFbHist + (size_t)max_fb_frames * kFbFrame) * sizeof(double) <=
                              hp_whole_budget_bytes &&
                          rec_bytes_all <= record_budget_bytes;
+      if (whole && (size_t)n_streams * (kFbHist + (size_t)max_fb_frames * kFbFrame) > hp_cap) {
+        // the whole-item buffer is an optimisation: if the device cannot hold it next to the
+        // caller's PCM, fall back to the chunked path instead of failing the batch
+        const size_t need = (size_t)n_streams * (kFbHist + (size_t)max_fb_frames * kFbFrame);
+        if (d_hp) PEAQ_CUDA(cudaFree(d_hp));
+        d_hp = nullptr;
+        hp_cap = 0;
+        if (cudaMalloc(&d_hp, need * sizeof(double)) == cudaSuccess) {
+          hp_cap = need;
+        } else {
+          cudaGetLastError();
+          d_hp = nullptr;
+          whole = false;
+        }
+      }
       const size_t hp_stride = kFbHist + (whole ? (size_t)max_fb_frames : chunk) * kFbFrame;
       if ((rc = ensure(&d_hp, &hp_cap, (size_t)n_streams * hp_stride))) return rc;
       if ((size_t)n_streams * kHpStateDoubles > hp_state_cap && !reset_state)
@@ -582,7 +598,7 @@ struct Engine {
       if (whole) {
         PEAQ_CUDA(cudaEventRecord(ev_hp_ready, stream));          // plans uploaded, PCM resident, state fresh
         PEAQ_CUDA(cudaStreamWaitEvent(hp_stream, ev_hp_ready, 0));
-        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, 0ull, max_fb_frames * kFbFrame, d_hp, hp_stride,
+        PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, 0ull, 0ull, max_fb_frames * kFbFrame, d_hp, hp_stride,
                                d_hp_state, true, hp_stream));
         PEAQ_CUDA(cudaEventRecord(ev_hp_done, hp_stream));
         launches++;
@@ -597,6 +613,7 @@ struct Engine {
         }
         PEAQ_CUDA(cudaStreamWaitEvent(stream, ev_hp_done, 0));
       }
+      if (reset_state) fb_pos = 0;   // samples the filter-bank clock has consumed before this call (sessions continue)
       unsigned first = 0;
       while (first < max_fb_frames) {
         const unsigned n = (unsigned)std::min<size_t>(chunk, max_fb_frames - first);
@@ -604,8 +621,9 @@ struct Engine {
         if ((rc = timer_begin(7))) return rc;
         PEAQ_CUDA(launch_fb_flags(pcm_fb, n_pairs, first, n, d_fbflags, stream));
         if (!whole) {
-          PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame, samples, d_hp,
-                                 hp_stride, d_hp_state, first == 0 && reset_state, stream));
+          PEAQ_CUDA(launch_fb_hp(d_tables, pcm_fb, n_pairs, (unsigned long long)first * kFbFrame,
+                                 fb_pos + (unsigned long long)first * kFbFrame, samples, d_hp, hp_stride, d_hp_state,
+                                 first == 0 && reset_state, stream));
         }
         if ((rc = timer_end())) return rc;
         // PEAQ_B200_FB_DIRECT=1: all 40 filters as direct FIRs (development aid / cross-check)
@@ -626,6 +644,7 @@ struct Engine {
         if ((rc = timer_end())) return rc;
         first += n;
       }
+      fb_pos += (unsigned long long)max_fb_frames * kFbFrame;
       if (max_fb_frames == 0 && reset_state) {
         // publish the (empty) fb-clock MOVs so the epilogue sees 0/0 like the reference
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, 0, d_fbflags, pcm_fb.n_frames, 0, 0, d_state, A, nullptr,
@@ -1065,6 +1084,7 @@ struct Session {
     double level;
     uint64_t fifo_floats[2][2];
     uint64_t state_doubles, hp_doubles;
+    uint64_t fb_pos;   // samples the filter-bank clock has consumed (anchors the DC-reject block scan)
   };
   static constexpr uint32_t kSnapMagic = 0x51414550u;   // "PEAQ"
 
@@ -1095,6 +1115,7 @@ struct Session {
       }
     h.state_doubles = state_doubles();
     h.hp_doubles = hp_doubles();
+    h.fb_pos = engine ? engine->fb_pos : 0;
     total += (h.state_doubles + h.hp_doubles) * sizeof(double) + sizeof(PairResult);
     if (size) *size = total;
     if (!buf) return 0;
@@ -1146,6 +1167,7 @@ struct Session {
       if (rc) return rc;
       PEAQ_CUDA(cudaSetDevice(device));
       started = true;
+      engine->fb_pos = h.fb_pos;
       if (h.state_doubles != state_doubles() || h.hp_doubles != hp_doubles()) {
         started = false;
         return fail(PEAQ_B200_ERR_INVALID, "snapshot of another engine version");

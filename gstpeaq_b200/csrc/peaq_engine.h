@@ -21,7 +21,8 @@ constexpr int kMaxChannels = 2;
 constexpr int kNumAcc = 11;        // accumulator slots (11 basic MOVs; 5 used in advanced)
 constexpr int kAccFields = 8;      // num, den, x0, x1, x2, saved num, saved den, saved max
 constexpr int kBandStateFields = 14;
-constexpr int kHpStateDoubles = 6 + kFbHist + 2 * 3 * kFbRecBands;   // DC-reject filter state + FIR history per stream (even: 16-byte rows)
+constexpr int kHpHdr = 24;   // DC-reject scan state per stream, see peaq_fb.cu (FB1)
+constexpr int kHpStateDoubles = kHpHdr + kFbHist + 2 * 3 * kFbRecBands;   // + FIR history + filter-bank chain values (even: 16-byte rows)
 
 // Layout of one per-frame record written by K1 and read by K2 (units: doubles).
 struct RecordLayout {
@@ -157,8 +158,10 @@ cudaError_t launch_fused_basic(const DeviceTables* d_tables, PcmView pcm, int n_
 // advanced mode (peaq_fb.cu, peaq_scan_adv.cu)
 cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsigned n_chunk_frames,
                             unsigned char* flags, cudaStream_t stream);
+// t0: position of the chunk in the PCM buffers; pos0: its absolute position in the item (they
+// differ for streaming sessions, whose buffers hold only the newest samples)
 cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
-                         unsigned long long t0, unsigned chunk_samples,
+                         unsigned long long t0, unsigned long long pos0, unsigned chunk_samples,
                          double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
                          cudaStream_t stream);
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,

@@ -82,7 +82,40 @@ __global__ void fb_flags_kernel(PcmView pcm, unsigned first_frame, unsigned n_ch
 }
 
 // ---------------------------------------------------------------------------
-// FB1.  hp buffer per stream: [kFbHist history samples][chunk samples].
+// FB1: level scaling (fbearmodel.c:289) and the two cascaded DC-reject biquads
+// (fbearmodel.c:292-303).  hp buffer per stream: [kFbHist history samples][chunk samples].
+//
+// The recurrence is sequential in time: one sample costs a loop-carried chain of ~100 cycles,
+// 25 ms per 10 s of audio however many SMs idle -- 1.5 s for a batch of 10-minute items.  It is
+// therefore evaluated as a BLOCK SCAN over blocks of kHpL = 512 samples at ABSOLUTE positions
+// of the item (block j = samples [512 j, 512 j + 512)):
+//   e0[j]   = end state of block j run from a zero recursive state (its input history x[n-1],
+//             x[n-2] is PCM, not state)
+//   s0[j+1] = e0[j] + M s0[j]            M = homogeneous transition over 512 samples, s0[0] = 0
+//   e1[j]   = end state of block j run from s0[j]
+//   d[j+1]  = (e1[j] - s0[j+1]) + M d[j]                                              d[0] = 0
+//   output of block j = the reference's own recurrence started from s[j] = s0[j] + d[j]
+// The near-double pole of the sections makes M s cancel ~30:1, so s0 alone is ~1e-10 off; d is
+// the (tiny) correction, whose own cancellation no longer matters.  Against the purely
+// sequential recurrence the output differs by a rounding sequence: ~1e-11 of the signal level
+// (MOVs <= 3e-12, tests/test_gpu_parity.py).
+//
+// TWO kernels compute exactly this, operation for operation:
+//   fb_hp_kernel       one thread per stream walks the chunk sample by sample and carries all
+//                      three recurrences (they are independent chains: same latency as one);
+//                      any chunk start / length -- sessions, short chunks, huge batches
+//   fb_hp_par_*        blocks in parallel (passes 0, 1, 2) with the two sequential per-stream
+//                      scans in between; chunks that start on a block boundary -- few long items
+// and both leave the same state behind (kHpHdr doubles per stream):
+//   [0,1] x[n-1], x[n-2] | [2..5] output recurrence | [6..9] zero-state recurrence |
+//   [10..13] recurrence from s0 | [14..17] s0[j] | [18..21] d[j]      (j = current block)
+// so results do not depend on how an item is chunked, streamed or which kernel ran: every block
+// starts from the same numbers.
+constexpr int kHpL = 512;
+
+struct HpTransition {
+  double m[4][4];   // [to][from] over (y1a, y2a, y1b, y2b)
+};
 
 struct Biquads {
   double x1, x2, y1a, y2a, y1b, y2b;
@@ -98,21 +131,45 @@ struct Biquads {
     y1b = h2;
     return h2;
   }
+  __device__ __forceinline__ void set_y(const double (&s)[4]) { y1a = s[0]; y2a = s[1]; y1b = s[2]; y2b = s[3]; }
+  __device__ __forceinline__ void get_y(double (&s)[4]) const { s[0] = y1a; s[1] = y2a; s[2] = y1b; s[3] = y2b; }
 };
+
+// o = e + M s
+__device__ __forceinline__ void hp_apply(const HpTransition& M, const double (&s)[4], const double (&e)[4],
+                                         double (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    o[r] = fma(M.m[r][0], s[0], fma(M.m[r][1], s[1], fma(M.m[r][2], s[2], fma(M.m[r][3], s[3], e[r]))));
+}
+
+// block boundary: from (s0[j], d[j]) and the end states of block j to (s0[j+1], d[j+1])
+__device__ __forceinline__ void hp_block_update(const HpTransition& M, double (&s0)[4], double (&d)[4],
+                                                const double (&e0)[4], const double (&e1)[4]) {
+  double s0n[4], r[4], dn[4];
+  hp_apply(M, s0, e0, s0n);
+#pragma unroll
+  for (int k = 0; k < 4; k++) r[k] = e1[k] - s0n[k];   // nearly equal: exact
+  hp_apply(M, d, r, dn);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    s0[k] = s0n[k];
+    d[k] = dn[k];
+  }
+}
 
 constexpr int kHpBlock = 16;   // samples per register block (input prefetch / 128-byte output rows)
 
-// One thread per stream (pair, channel, side).  The recurrence is inherently sequential
-// in time and its loop-carried chain (multiply, add, add per section) is what bounds the
-// kernel, so a thread carries ONE filter: with both channels of a signal in one thread the
-// half-rate FP64 pipe of the (single) resident warp became the limit instead.  Input is
-// fetched 16 samples ahead with 128-bit loads (the two channel threads of a signal read the
-// same interleaved lines; the second read hits L1), output written as 128-byte rows.
+// One thread per stream (pair, channel, side), sample by sample.  Input is fetched 16 samples
+// ahead with 128-bit loads (the two channel threads of a signal read the same interleaved
+// lines; the second read hits L1), output written as 128-byte rows.
 template <int C>
 __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams,
                              unsigned long long t0, unsigned chunk_samples,
                              double* __restrict__ hp, size_t hp_stride,
-                             double* __restrict__ hp_state /* [stream][kHpStateDoubles] */, int first_chunk) {
+                             double* __restrict__ hp_state /* [stream][kHpStateDoubles] */, HpTransition M,
+                             unsigned long long pos0 /* absolute position of the chunk's first sample in the item */,
+                             int first_chunk) {
   const int stream = blockIdx.x * blockDim.x + threadIdx.x;   // pair * 2C + 2c + side, as everywhere
   if (stream >= n_streams) return;
   const int pair = stream / (2 * C), c = (stream >> 1) % C, side = stream & 1;
@@ -121,11 +178,22 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   const bool aligned = (reinterpret_cast<uintptr_t>(sig) & 15) == 0;
   double* out = hp + (size_t)stream * hp_stride;
   double* st = hp_state + (size_t)stream * kHpStateDoubles;
-  Biquads f = first_chunk ? Biquads{0, 0, 0, 0, 0, 0} : Biquads{st[0], st[1], st[2], st[3], st[4], st[5]};
+  Biquads fo = Biquads{0, 0, 0, 0, 0, 0}, f0 = fo, f1 = fo;   // output, zero-state, from-s0 recurrences
+  double s0[4] = {0., 0., 0., 0.}, d[4] = {0., 0., 0., 0.};
+  if (!first_chunk) {
+    fo = Biquads{st[0], st[1], st[2], st[3], st[4], st[5]};
+    f0 = Biquads{st[0], st[1], st[6], st[7], st[8], st[9]};
+    f1 = Biquads{st[0], st[1], st[10], st[11], st[12], st[13]};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      s0[k] = st[14 + k];
+      d[k] = st[18 + k];
+    }
+  }
   {
     // history for the FIR bank: last kFbHist samples of the previous chunk
     double2* o2 = reinterpret_cast<double2*>(out);
-    const double2* src = reinterpret_cast<const double2*>(st + 6);   // saved by the previous chunk
+    const double2* src = reinterpret_cast<const double2*>(st + kHpHdr);   // saved by the previous chunk
     for (int i = 0; i < kFbHist / 2; i++) o2[i] = first_chunk ? make_double2(0., 0.) : src[i];
   }
   const double lf = T->level_factor_fb;
@@ -171,40 +239,50 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
     if (i0 + kHpBlock < chunk_samples) fetch(i0 + kHpBlock);
     double y[kHpBlock];
 #pragma unroll
-    for (int k = 0; k < kHpBlock; k++) y[k] = f.step(x[k] * lf);   // fbearmodel.c:289
+    for (int k = 0; k < kHpBlock; k++) {
+      const double scaled = x[k] * lf;   // fbearmodel.c:289
+      y[k] = fo.step(scaled);
+      f0.step(scaled);
+      f1.step(scaled);
+    }
     double2* o = reinterpret_cast<double2*>(out + kFbHist + i0);
 #pragma unroll
     for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[2 * k], y[2 * k + 1]);
+    // chunks are whole 192-sample frames, so the 16-sample groups tile the 512-sample blocks
+    if (((pos0 + i0 + kHpBlock) & (kHpL - 1)) == 0) {
+      double e0[4], e1[4], s[4];
+      f0.get_y(e0);
+      f1.get_y(e1);
+      hp_block_update(M, s0, d, e0, e1);
+#pragma unroll
+      for (int k = 0; k < 4; k++) s[k] = s0[k] + d[k];
+      const double z[4] = {0., 0., 0., 0.};
+      fo.set_y(s);
+      f0.set_y(z);
+      f1.set_y(s0);
+    }
   }
-  st[0] = f.x1; st[1] = f.x2; st[2] = f.y1a; st[3] = f.y2a; st[4] = f.y1b; st[5] = f.y2b;
+  st[0] = fo.x1; st[1] = fo.x2;
+  st[2] = fo.y1a; st[3] = fo.y2a; st[4] = fo.y1b; st[5] = fo.y2b;
+  st[6] = f0.y1a; st[7] = f0.y2a; st[8] = f0.y1b; st[9] = f0.y2b;
+  st[10] = f1.y1a; st[11] = f1.y2a; st[12] = f1.y1b; st[13] = f1.y2b;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    st[14 + k] = s0[k];
+    st[18 + k] = d[k];
+  }
   // the last kFbHist filtered samples ([history | chunk] is contiguous in `out`) become
   // the next chunk's history; works for chunks shorter than the history too
-  double2* dst = reinterpret_cast<double2*>(st + 6);
+  double2* dst = reinterpret_cast<double2*>(st + kHpHdr);
   const double2* src = reinterpret_cast<const double2*>(out + chunk_samples);
   for (int i = 0; i < kFbHist / 2; i++) dst[i] = src[i];
 }
 
-// ---------------------------------------------------------------------------
-// FB1p: the same filter as a TIME-PARALLEL block scan -- opt-in (PEAQ_B200_HP_PARALLEL=1), for
-// few, long items, where the exact recurrence above keeps a handful of threads busy for
-// 52 ns per sample.  The chunk is cut into blocks of kHpL samples:
-//   pass 0   every block from a zero recursive state (its input history x[n-1], x[n-2] is PCM,
-//            not state) -> zero-state end state e0[j]
-//   scan 0   per stream: s0[j+1] = e0[j] + M s0[j], M = homogeneous transition over kHpL samples
-//   pass 1   every block from s0[j] -> end state e1[j]
-//   scan 1   d[j+1] = (e1[j] - s0[j+1]) + M d[j];  s[j+1] = s0[j+1] + d[j+1]
-//   pass 2   every block from s[j] with the reference's own recurrence -> output
-// The near-double pole of the sections makes M s cancel ~30:1, so s0 alone is ~1e-10 off; the
-// refinement solves for the (tiny) correction d, whose own cancellation no longer matters.  What
-// remains is a different rounding sequence from the purely sequential run: ~1e-11 of the signal
-// level, i.e. up to ~1e-8 in bands 60 dB below it -- inside the 1e-6 bar of the MOVs, but not
-// the 1e-12 the default path keeps, hence opt-in.
-constexpr int kHpL = 512;
-
-struct HpTransition {
-  double m[4][4];   // [to][from] over (y1a, y2a, y1b, y2b)
-};
-
+// ---- the same block scan with the blocks in parallel (chunks starting on a block boundary) ----
+// starts/ends: [stream][n_blocks + 1][4]; MODE 0: zero-state pass -> ends; MODE 1: pass from
+// starts (= s0) -> ends; MODE 2: output pass from starts (= s0 + d).  The last block may be
+// partial (end of the chunk): its recurrences stop exactly at the chunk's end and their running
+// states go to the stream's state header, like fb_hp_kernel leaves them.
 template <int C, int MODE>
 __global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams, int n_blocks,
                                        unsigned long long t0, unsigned chunk_samples,
@@ -226,83 +304,102 @@ __global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmVi
     if (!first_chunk) {
       f.x1 = st[0];
       f.x2 = st[1];
-      if (MODE != 0) { f.y1a = st[2]; f.y2a = st[3]; f.y1b = st[4]; f.y2b = st[5]; }
     }
   } else {
     const unsigned long long s1 = t0 + b0 - 1, s2 = t0 + b0 - 2;
     f.x1 = (s1 < n ? __ldg(sig + s1 * C + c) : 0.f) * lf;
     f.x2 = (s2 < n ? __ldg(sig + s2 * C + c) : 0.f) * lf;
-    if (MODE != 0) {
-      const double* bs = starts + ((size_t)stream * n_blocks + blk) * 4;
-      f.y1a = bs[0]; f.y2a = bs[1]; f.y1b = bs[2]; f.y2b = bs[3];
-    }
+  }
+  if (MODE != 0) {
+    const double* bs = starts + ((size_t)stream * (n_blocks + 1) + blk) * 4;
+    f.y1a = bs[0]; f.y2a = bs[1]; f.y1b = bs[2]; f.y2b = bs[3];
   }
   double* out = hp + (size_t)stream * hp_stride + kFbHist + b0;
-  for (unsigned i0 = 0; i0 < len; i0 += kHpBlock) {
+  for (unsigned i0 = 0; i0 < len; i0 += kHpBlock) {   // len is a multiple of 16 (whole frames)
     double y[kHpBlock];
 #pragma unroll
     for (int k = 0; k < kHpBlock; k++) {
       const unsigned long long s = t0 + b0 + i0 + k;
-      const float x = (i0 + k < len && s < n) ? __ldg(sig + s * C + c) : 0.f;
+      const float x = s < n ? __ldg(sig + s * C + c) : 0.f;
       y[k] = f.step(x * lf);   // fbearmodel.c:289
     }
     if (MODE == 2) {
-      if (i0 + kHpBlock <= len) {
-        double2* o = reinterpret_cast<double2*>(out + i0);
+      double2* o = reinterpret_cast<double2*>(out + i0);
 #pragma unroll
-        for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[2 * k], y[2 * k + 1]);
-      } else {
-        for (int k = 0; k < kHpBlock && i0 + k < len; k++) out[i0 + k] = y[k];
-      }
+      for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[2 * k], y[2 * k + 1]);
     }
   }
-  if (MODE != 2) {
-    // (only full blocks feed the scans; the states past a partial last block are never used --
-    // but its recurrence ran kHpBlock-padded with zeros, so do not publish it)
-    double* be = ends + ((size_t)stream * n_blocks + blk) * 4;
+  if (MODE != 2 && len == (unsigned)kHpL) {
+    double* be = ends + ((size_t)stream * (n_blocks + 1) + blk) * 4;
     be[0] = f.y1a; be[1] = f.y2a; be[2] = f.y1b; be[3] = f.y2b;
-  } else if (blk == n_blocks - 1) {
-    st[0] = f.x1; st[1] = f.x2; st[2] = f.y1a; st[3] = f.y2a; st[4] = f.y1b; st[5] = f.y2b;
+  }
+  if (blk == n_blocks - 1) {
+    // running states at the end of the chunk; when the last block is full the scans have already
+    // moved on to the next block and fb_hp_par_scan_kernel<1> writes the header instead
+    if (MODE == 2) { st[0] = f.x1; st[1] = f.x2; }
+    if (len < (unsigned)kHpL) {
+      const int o = MODE == 2 ? 2 : (MODE == 0 ? 6 : 10);
+      st[o] = f.y1a; st[o + 1] = f.y2a; st[o + 2] = f.y1b; st[o + 3] = f.y2b;
+    }
   }
 }
 
-// MODE 0: zero-state end states (in `a`) -> approximate start states, in place.
-// MODE 1: refinement; `a` holds the approximate starts, `b` the end states reached from them.
+// MODE 0: a = zero-state end states e0[j] -> a = s0[j], j = 0..n_blocks (in place).
+// MODE 1: a = s0[j], b = e1[j] -> a = s[j] = s0[j] + d[j]; leaves (s0, d) of the block the chunk
+//         ends in -- and, if that block has not begun yet, its three start states -- in the header.
 template <int MODE>
-__global__ void fb_hp_par_scan_kernel(int n_streams, int n_blocks, const double* __restrict__ hp_state,
-                                      double* __restrict__ a, const double* __restrict__ b, HpTransition M,
-                                      int first_chunk) {
+__global__ void fb_hp_par_scan_kernel(int n_streams, int n_blocks, unsigned chunk_samples,
+                                      double* __restrict__ hp_state, double* __restrict__ a,
+                                      const double* __restrict__ b, HpTransition M, int first_chunk) {
   const int stream = blockIdx.x * blockDim.x + threadIdx.x;
   if (stream >= n_streams) return;
-  double* pa = a + (size_t)stream * n_blocks * 4;
-  auto apply = [&](const double (&s)[4], const double (&e)[4], double (&o)[4]) {
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-      o[r] = fma(M.m[r][0], s[0], fma(M.m[r][1], s[1], fma(M.m[r][2], s[2], fma(M.m[r][3], s[3], e[r]))));
-  };
+  double* pa = a + (size_t)stream * (n_blocks + 1) * 4;
+  double* st = hp_state + (size_t)stream * kHpStateDoubles;
+  const int n_full = (int)(chunk_samples / kHpL);   // n_blocks or n_blocks - 1
   if (MODE == 0) {
-    const double* st = hp_state + (size_t)stream * kHpStateDoubles;
     double s[4] = {0., 0., 0., 0.};
-    if (!first_chunk) { s[0] = st[2]; s[1] = st[3]; s[2] = st[4]; s[3] = st[5]; }
-    for (int j = 0; j < n_blocks; j++) {
-      const double e[4] = {pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]};
+    if (!first_chunk) { s[0] = st[14]; s[1] = st[15]; s[2] = st[16]; s[3] = st[17]; }
+    for (int j = 0; j <= n_full; j++) {
+      const double e[4] = {pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]};   // (j = n_full: unused)
       pa[4 * j] = s[0]; pa[4 * j + 1] = s[1]; pa[4 * j + 2] = s[2]; pa[4 * j + 3] = s[3];
-      double o[4];
-      apply(s, e, o);
-      s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+      if (j < n_full) {
+        double o[4];
+        hp_apply(M, s, e, o);
+        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+      }
     }
   } else {
-    const double* pb = b + (size_t)stream * n_blocks * 4;
-    double d[4] = {0., 0., 0., 0.};   // block 0 starts from the exact carried state
-    for (int j = 0; j + 1 < n_blocks; j++) {
-      double r[4], o[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) r[k] = pb[4 * j + k] - pa[4 * (j + 1) + k];   // nearly equal: exact
-      apply(d, r, o);
+    const double* pb = b + (size_t)stream * (n_blocks + 1) * 4;
+    double d[4] = {0., 0., 0., 0.};
+    if (!first_chunk) { d[0] = st[18]; d[1] = st[19]; d[2] = st[20]; d[3] = st[21]; }
+    double s0[4] = {pa[0], pa[1], pa[2], pa[3]};
+    for (int j = 0; j <= n_full; j++) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        d[k] = o[k];
-        pa[4 * (j + 1) + k] += d[k];
+        s0[k] = pa[4 * j + k];
+        pa[4 * j + k] = s0[k] + d[k];
+      }
+      if (j < n_full) {
+        double r[4], o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = pb[4 * j + k] - pa[4 * (j + 1) + k];   // e1[j] - s0[j+1]: nearly equal, exact
+        hp_apply(M, d, r, o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = o[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      st[14 + k] = s0[k];
+      st[18 + k] = d[k];
+    }
+    if (n_full == n_blocks) {
+      // the chunk ends on a block boundary: the next block starts from (s, 0, s0)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        st[2 + k] = s0[k] + d[k];
+        st[6 + k] = 0.;
+        st[10 + k] = s0[k];
       }
     }
   }
@@ -312,13 +409,13 @@ __global__ void fb_hp_par_hist_kernel(double* __restrict__ hp, size_t hp_stride,
                                       unsigned chunk_samples, int mode, int first_chunk) {
   const int stream = blockIdx.x;
   double2* buf = reinterpret_cast<double2*>(hp + (size_t)stream * hp_stride);
-  double2* st = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + 6);
+  double2* st = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + kHpHdr);
   if (mode == 0) {
     for (int i = threadIdx.x; i < kFbHist / 2; i += blockDim.x) buf[i] = first_chunk ? make_double2(0., 0.) : st[i];
   } else {
     // [history | chunk] is contiguous: the last kFbHist filtered samples, also for short chunks
     const double* src = hp + (size_t)stream * hp_stride + chunk_samples;
-    double* dst = hp_state + (size_t)stream * kHpStateDoubles + 6;
+    double* dst = hp_state + (size_t)stream * kHpStateDoubles + kHpHdr;
     for (int i = threadIdx.x; i < kFbHist; i += blockDim.x) dst[i] = src[i];
   }
 }
@@ -519,7 +616,7 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2* xch = reinterpret_cast<double2*>(xs_raw + kRecXsDoubles) + warp * 96;   // [3][32]
   const double* __restrict__ src = hp + (size_t)stream * hp_stride + kFbHist;
-  double2* carry_state = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + 6 + kFbHist);
+  double2* carry_state = reinterpret_cast<double2*>(hp_state + (size_t)stream * kHpStateDoubles + kHpHdr + kFbHist);
   const int n_slots = warp + (kRecSlots - 1) * kRecWarps < kFbRecBands ? kRecSlots : kRecSlots - 1;
   // chain values of this warp's bands: [slot][frequency], kept in shared memory between tiles
   double2* cst = reinterpret_cast<double2*>(xs_raw + kRecXsDoubles) + kRecWarps * 96 + warp * (3 * kRecSlots);
@@ -662,50 +759,55 @@ cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsi
 }
 
 cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
-                         unsigned long long t0, unsigned chunk_samples,
+                         unsigned long long t0, unsigned long long pos0, unsigned chunk_samples,
                          double* hp, size_t hp_stride, double* hp_state, bool first_chunk,
                          cudaStream_t stream) {
   const int n_streams = n_pairs * 2 * pcm.channels;
   if (n_streams <= 0) return cudaSuccess;
-  static const bool parallel = std::getenv("PEAQ_B200_HP_PARALLEL") && std::atoi(std::getenv("PEAQ_B200_HP_PARALLEL"));
-  if (parallel && chunk_samples >= 4 * kHpL) {
-    // time-parallel block scan (see FB1p above); scratch from the stream-ordered allocator
-    static const HpTransition M = [] {
-      HpTransition t;
-      for (int from = 0; from < 4; from++) {
-        double v[4] = {0., 0., 0., 0.};
-        v[from] = 1.;
-        for (int i = 0; i < kHpL; i++) {
-          const double h1 = 1.99517 * v[0] - 0.995174 * v[1];
-          const double h2 = h1 - 2. * v[0] + v[1] + 1.99799 * v[2] - 0.997998 * v[3];
-          v[1] = v[0]; v[0] = h1; v[3] = v[2]; v[2] = h2;
-        }
-        for (int to = 0; to < 4; to++) t.m[to][from] = v[to];
+  // homogeneous transition of the recursive state over one block of kHpL samples
+  static const HpTransition M = [] {
+    HpTransition t;
+    for (int from = 0; from < 4; from++) {
+      double v[4] = {0., 0., 0., 0.};
+      v[from] = 1.;
+      for (int i = 0; i < kHpL; i++) {
+        const double h1 = 1.99517 * v[0] - 0.995174 * v[1];
+        const double h2 = h1 - 2. * v[0] + v[1] + 1.99799 * v[2] - 0.997998 * v[3];
+        v[1] = v[0]; v[0] = h1; v[3] = v[2]; v[2] = h2;
       }
-      return t;
-    }();
+      for (int to = 0; to < 4; to++) t.m[to][from] = v[to];
+    }
+    return t;
+  }();
+  // Blocks in parallel when the sample-by-sample walk would leave the GPU idle: it keeps one
+  // thread per stream busy for ~52 ns per sample whatever the batch, the parallel form does three
+  // times the arithmetic on every SM.  Same results either way (PEAQ_B200_HP_PARALLEL=0/1 forces one).
+  static const int forced = std::getenv("PEAQ_B200_HP_PARALLEL") ? std::atoi(std::getenv("PEAQ_B200_HP_PARALLEL")) : -1;
+  const bool can = chunk_samples >= 4 * kHpL && pos0 % kHpL == 0;
+  const bool parallel = can && (forced == 1 || (forced < 0 && n_streams <= 4096));
+  if (parallel) {
     const int n_blocks = (int)((chunk_samples + kHpL - 1) / kHpL);
-    const size_t n_state = (size_t)n_streams * n_blocks * 4;
-    double *sa = nullptr, *sb = nullptr;
+    const size_t n_state = (size_t)n_streams * (n_blocks + 1) * 4;
+    double *sa = nullptr, *sb = nullptr;   // scratch from the stream-ordered allocator
     cudaError_t e = cudaMallocAsync(&sa, n_state * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     e = cudaMallocAsync(&sb, n_state * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     const int fc = first_chunk ? 1 : 0;
     const long long n_threads = (long long)n_streams * n_blocks;
-    const unsigned grid = (unsigned)((n_threads + 63) / 64), sgrid = (unsigned)((n_streams + 63) / 64);
+    const unsigned grid = (unsigned)((n_threads + 63) / 64), sgrid = (unsigned)((n_streams + 31) / 32);
     fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 0, fc);
     if (pcm.channels == 2) {
       fb_hp_par_block_kernel<2, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
-      fb_hp_par_scan_kernel<0><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_scan_kernel<0><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<2, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
-      fb_hp_par_scan_kernel<1><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_scan_kernel<1><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<2, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
     } else {
       fb_hp_par_block_kernel<1, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
-      fb_hp_par_scan_kernel<0><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_scan_kernel<0><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<1, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
-      fb_hp_par_scan_kernel<1><<<sgrid, 64, 0, stream>>>(n_streams, n_blocks, hp_state, sa, sb, M, fc);
+      fb_hp_par_scan_kernel<1><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<1, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
     }
     fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 1, fc);
@@ -717,11 +819,11 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
   const int block = 32;
   const int grid = (n_streams + block - 1) / block;
   if (pcm.channels == 2) {
-    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_streams, t0, chunk_samples, hp, hp_stride, hp_state,
-                                                first_chunk ? 1 : 0);
+    fb_hp_kernel<2><<<grid, block, 0, stream>>>(d_tables, pcm, n_streams, t0, chunk_samples, hp, hp_stride, hp_state, M,
+                                                pos0, first_chunk ? 1 : 0);
   } else {
-    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_streams, t0, chunk_samples, hp, hp_stride, hp_state,
-                                                first_chunk ? 1 : 0);
+    fb_hp_kernel<1><<<grid, block, 0, stream>>>(d_tables, pcm, n_streams, t0, chunk_samples, hp, hp_stride, hp_state, M,
+                                                pos0, first_chunk ? 1 : 0);
   }
   return cudaGetLastError();
 }

@@ -17,7 +17,11 @@ def pytest_configure(config):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     if not (os.path.exists(os.path.join(ROOT, "gstpeaq_b200", "libpeaq_b200.so"))
             and os.path.exists(os.path.join(ROOT, "gstpeaq_b200", "peaq"))):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "gstpeaq_b200", "csrc")])
+        import shutil
+        if shutil.which("nvcc"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "gstpeaq_b200", "csrc")])
+        # without nvcc the tests that need the library fail on their own with the loader's message
+        # ("... is missing: build it with make ..."); the oracle-only tests still run
     if (not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpeaq_ref.so"))
             and os.path.isdir("/root/reference/src")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])

@@ -477,9 +477,12 @@ def test_unaligned_mono_batch_matches_oracle(advanced):
         check_result(out[p], want, "mono pair %d len %d adv %d" % (p, n, advanced))
 
 
-def test_time_parallel_dc_reject_scan_option():
-    """PEAQ_B200_HP_PARALLEL=1 (block scan with refinement, for few long items) against the
-    default exact recurrence: excitations to 5e-9, MOVs / ODG to 1e-9 (measured 4e-10 / 3e-12)"""
+def test_dc_reject_block_scan_same_bits_sequential_and_parallel():
+    """FB1 is a block scan over absolute 512-sample blocks with two implementations -- one thread
+    per stream walking the samples (sessions, big batches) and blocks in parallel (few long
+    items).  Both must produce the SAME bits, whatever the chunking: per-frame excitations of a
+    ragged batch, whole-item and chunked, forced through either kernel; and the oracle's (exact
+    sequential) excitations are matched to 5e-9 (the block scan's rounding sequence differs)."""
     import json
     import os
     import subprocess
@@ -490,25 +493,45 @@ sys.path.insert(0, %r); sys.path.insert(0, %r)
 import gstpeaq_b200 as G
 from signals import synth_pair
 ch = 2
-ref, test = synth_pair(77, 96000, ch)
+lengths = [96000, 70001, 50000]
+stride = max(lengths) * ch
+ref = np.zeros((3, stride), np.float32); test = np.zeros_like(ref)
+for p, n in enumerate(lengths):
+    r, t = synth_pair(77 + p, n, ch)
+    ref[p, :n * ch] = r; test[p, :n * ch] = t
 e = G.Engine(0, advanced=True)
 e.keep_records(True)
-out = e.run_host(ref, test, ch)
-exc, movs = e.fb_debug(1, ch)
-print(json.dumps({"movs": out["movs"][0][:5].tolist(), "odg": float(out["odg"][0]),
-                  "exc": np.asarray(exc[0]).ravel().tolist()}))
+out = e.run_host(ref, test, ch, n_samples=np.array(lengths, np.uint64))
+exc, movs = e.fb_debug(3, ch)
+e2 = G.Engine(0, advanced=True)      # chunked (PEAQ_B200_FB_BUDGET_MB from the environment applies to both)
+out2 = e2.run_host(ref, test, ch, n_samples=np.array(lengths, np.uint64))
+print(json.dumps({"movs": out["movs"][:, :5].tolist(), "odg": out["odg"].tolist(), "odg2": out2["odg"].tolist(),
+                  "exc": np.asarray(exc).ravel().tolist()}))
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for par in ("0", "1"):
+    for par, budget in (("0", ""), ("1", ""), ("1", "1"), ("0", "1")):
         env = dict(os.environ, PEAQ_B200_HP_PARALLEL=par)
+        if budget:
+            env["PEAQ_B200_FB_BUDGET_MB"] = budget      # a few frames per chunk
         p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, p.stderr[-2000:]
-        res[par] = json.loads(p.stdout.strip().splitlines()[-1])
-    a, b = res["0"], res["1"]
-    assert a["exc"] != b["exc"]          # the option really took the other path
-    np.testing.assert_allclose(a["exc"], b["exc"], rtol=5e-9)
-    np.testing.assert_allclose(a["movs"], b["movs"], rtol=1e-9, atol=1e-12)
-    assert abs(a["odg"] - b["odg"]) < 1e-9
+        res[par + budget] = json.loads(p.stdout.strip().splitlines()[-1])
+    a = res["0"]
+    for k in ("1", "11", "01"):
+        assert res[k]["odg"] == a["odg"] and res[k]["movs"] == a["movs"], k
+        assert res[k]["odg2"] == a["odg"], k
+    assert res["1"]["exc"] == a["exc"]
+    # against the oracle's sequential recurrence
+    ch = 2
+    r, t = synth_pair(77, 96000, ch)
+    o = H.OraclePeaq(True, 92.0, ch, fb_trace=600)
+    o.push(r, t)
+    o.finish()
+    nfb = o.result()["frames_fb"]
+    exc = np.asarray(a["exc"]).reshape(3, -1, 2 * ch, 2, 40)[0, :nfb]
+    want = o.fb_trace["excitation"][:nfb]           # [frame][side][channel][band]
+    got = exc[:, :, 1, :].reshape(nfb, ch, 2, 40).transpose(0, 2, 1, 3)    # stream = 2 * channel + side
+    np.testing.assert_allclose(got, want, rtol=5e-9)
 
 
 def _engine_with_env(monkeypatch, advanced=False, **env):
