@@ -181,6 +181,16 @@ struct Engine {
   int pipeline_mode = -1;   // PEAQ_B200_PIPELINE: 1 always, 0 never, default: batches of few pairs
   cudaStream_t scan_stream = nullptr;
   cudaEvent_t ev_rec_ready[2] = {nullptr, nullptr}, ev_rec_free[2] = {nullptr, nullptr};
+  // segments of long items (peaq_segments.cu): device copies of the segment table
+  int segment_mode = 1;   // PEAQ_B200_SEGMENTS=0: never cut items into segments
+  unsigned long long* d_seg_base = nullptr;
+  size_t seg_base_cap = 0;
+  unsigned* d_seg_words = nullptr;   // [5][n_vp]: segment index, frame0 / acc_start of both clocks; then [2][n_items]
+  size_t seg_words_cap = 0;
+  unsigned char* d_seg_redo = nullptr;
+  size_t seg_redo_cap = 0;
+  PairResult* d_item_results = nullptr;
+  size_t item_results_cap = 0;
 
   int init() {
     PEAQ_CUDA(cudaSetDevice(device));
@@ -205,6 +215,7 @@ struct Engine {
     PEAQ_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     if (const char* env = std::getenv("PEAQ_B200_FUSED")) fused_mode = std::atoi(env) ? 1 : 0;
     if (const char* env = std::getenv("PEAQ_B200_PIPELINE")) pipeline_mode = std::atoi(env) ? 1 : 0;
+    if (const char* env = std::getenv("PEAQ_B200_SEGMENTS")) segment_mode = std::atoi(env) ? 1 : 0;
     if (const char* env = std::getenv("PEAQ_B200_RECORD_BUDGET_MB")) {
       const long mb = std::atol(env);
       if (mb > 0) record_budget_bytes = (size_t)mb << 20;
@@ -250,6 +261,10 @@ struct Engine {
     cudaFree(d_records);
     cudaFree(d_state);
     cudaFree(d_results);
+    cudaFree(d_seg_base);
+    cudaFree(d_seg_words);
+    cudaFree(d_seg_redo);
+    cudaFree(d_item_results);
     cudaFree(d_nsamples);
     cudaFree(d_nframes);
     for (int i = 0; i < 2; i++) {
@@ -470,6 +485,42 @@ struct Engine {
     return 0;
   }
 
+  // Host description of a batch cut into segments (peaq_segments.cu): one entry per virtual pair
+  // (an item's segments are consecutive), plus first_vp / n_seg per item.
+  struct SegPlan {
+    int n_items = 0;
+    std::vector<unsigned long long> base;   // floats from the batch's ref / test pointers
+    std::vector<unsigned> seg_index, frame0_fft, acc_start_fft, frame0_fb, acc_start_fb;
+    std::vector<unsigned> first_vp, n_seg;
+  };
+
+  int upload_segments(const SegPlan& sp, int n_vp, SegTable* t) {
+    int rc;
+    if ((rc = ensure(&d_seg_base, &seg_base_cap, (size_t)n_vp))) return rc;
+    if ((rc = ensure(&d_seg_words, &seg_words_cap, (size_t)5 * n_vp + (size_t)2 * sp.n_items))) return rc;
+    plan_hold_ns.emplace_back(sp.base);
+    PEAQ_CUDA(cudaMemcpyAsync(d_seg_base, plan_hold_ns.back().data(), (size_t)n_vp * sizeof(unsigned long long),
+                              cudaMemcpyHostToDevice, stream));
+    std::vector<unsigned> words;
+    words.reserve((size_t)5 * n_vp + (size_t)2 * sp.n_items);
+    for (const auto* v : {&sp.seg_index, &sp.frame0_fft, &sp.acc_start_fft, &sp.frame0_fb, &sp.acc_start_fb})
+      words.insert(words.end(), v->begin(), v->end());
+    words.insert(words.end(), sp.first_vp.begin(), sp.first_vp.end());
+    words.insert(words.end(), sp.n_seg.begin(), sp.n_seg.end());
+    plan_hold_nf.emplace_back(std::move(words));
+    PEAQ_CUDA(cudaMemcpyAsync(d_seg_words, plan_hold_nf.back().data(), plan_hold_nf.back().size() * sizeof(unsigned),
+                              cudaMemcpyHostToDevice, stream));
+    const unsigned* w = d_seg_words;
+    t->seg_index = reinterpret_cast<const int*>(w);
+    t->frame0_fft = w + (size_t)n_vp;
+    t->acc_start_fft = w + (size_t)2 * n_vp;
+    t->frame0_fb = w + (size_t)3 * n_vp;
+    t->acc_start_fb = w + (size_t)4 * n_vp;
+    t->first_vp = reinterpret_cast<const int*>(w + (size_t)5 * n_vp);
+    t->n_seg = reinterpret_cast<const int*>(w + (size_t)5 * n_vp + sp.n_items);
+    return 0;
+  }
+
   // Runs the frames described by the plan(s) for `n_pairs` pairs whose PCM is
   // resident on the device, reading from sample 0 of the given buffers.
   // reset_state: start from fresh state (else continue a session).
@@ -477,7 +528,9 @@ struct Engine {
                        int C, const ClockPlan& fft, const ClockPlan& fb, bool reset_state,
                        PairResult* h_out, PairResult* d_out = nullptr, bool blocking = true,
                        const float* d_ref_fb = nullptr, const float* d_test_fb = nullptr,
-                       size_t pair_stride_fb = 0) {
+                       size_t pair_stride_fb = 0, const SegPlan* seg = nullptr, unsigned char* h_redo = nullptr) {
+    // seg: the n_pairs "pairs" are segments of seg->n_items items (peaq_segments.cu); results
+    // (h_out / d_out) are then per ITEM, h_redo[item] tells which items must be run again whole
     // d_ref_fb/d_test_fb: separate buffers for the filter-bank clock (streaming sessions
     // hold different windows of the stream per clock); default: the same buffers
     // d_out: where the kernels write the results (default: the engine's buffer);
@@ -494,8 +547,14 @@ struct Engine {
       if (advanced) max_fb_frames = std::max(max_fb_frames, fb.nf[p]);
     }
     if ((rc = upload_plan(fft, n_pairs, 0))) return rc;
-    const PcmView pcm = make_view(d_ref, d_test, pair_stride, C, 0);
+    PcmView pcm = make_view(d_ref, d_test, pair_stride, C, 0);
     PairResult* d_res = d_out ? d_out : d_results;
+    SegTable seg_table = {};
+    if (seg) {
+      if ((rc = upload_segments(*seg, n_pairs, &seg_table))) return rc;
+      pcm.base = d_seg_base;
+      d_res = d_results;   // per segment; the items' rows are gathered at the end
+    }
 
     if (!advanced) {
       if (reset_state) {
@@ -504,6 +563,10 @@ struct Engine {
         init_state_kernel<<<blocks, 256, 0, stream>>>(d_state, S, n_pairs);
         PEAQ_CUDA(cudaGetLastError());
         launches++;
+        if (seg) {
+          PEAQ_CUDA(launch_seg_init(d_state, &S, nullptr, n_pairs, seg_table, stream));
+          launches++;
+        }
       }
       // Two paths, same arithmetic, same bits (tests/test_gpu_parity.py):
       //  - frame-parallel K1 + per-pair K2 over chunks of per-frame records (default), and
@@ -531,11 +594,16 @@ struct Engine {
       }
     } else {
       if ((rc = upload_plan(fb, n_pairs, 1))) return rc;
-      const PcmView pcm_fb = make_view(d_ref_fb ? d_ref_fb : d_ref, d_test_fb ? d_test_fb : d_test,
-                                       d_ref_fb ? pair_stride_fb : pair_stride, C, 1);
+      PcmView pcm_fb = make_view(d_ref_fb ? d_ref_fb : d_ref, d_test_fb ? d_test_fb : d_test,
+                                 d_ref_fb ? pair_stride_fb : pair_stride, C, 1);
+      if (seg) pcm_fb.base = d_seg_base;
       if (reset_state) {
         PEAQ_CUDA(launch_init_adv_state(d_state, A, n_pairs, stream));
         launches++;
+        if (seg) {
+          PEAQ_CUDA(launch_seg_init(d_state, nullptr, &A, n_pairs, seg_table, stream));
+          launches++;
+        }
       }
       // ---- filter-bank clock: chunks of 192-sample frames -----------------------
       const int n_streams = n_pairs * 2 * C;
@@ -669,11 +737,104 @@ struct Engine {
       }
     }
 
+    int n_out = n_pairs;
+    if (seg) {
+      // sums of the segments -> segment 0 of every item, the scan kernels' epilogues once more
+      // (zero frames) on the combined state, then one result row per item
+      n_out = seg->n_items;
+      if ((rc = ensure(&d_seg_redo, &seg_redo_cap, (size_t)n_out))) return rc;
+      if ((rc = ensure(&d_item_results, &item_results_cap, (size_t)n_out))) return rc;
+      if (!advanced) {
+        PEAQ_CUDA(launch_seg_combine(d_state, &S, nullptr, n_out, seg_table, d_seg_redo, stream));
+        PEAQ_CUDA(launch_scan_basic(d_tables, d_records, L, pcm.n_frames, 0, 0, d_state, S, d_res, n_pairs, stream));
+        launches += 2;
+      } else {
+        PEAQ_CUDA(launch_seg_combine(d_state, nullptr, &A, n_out, seg_table, d_seg_redo, stream));
+        PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, 0, d_fbflags, pcm.n_frames, 0, 0, d_state, A, nullptr, n_pairs,
+                                 stream));
+        PEAQ_CUDA(launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, 0, 0, d_state, A, d_res, n_pairs, stream));
+        launches += 3;
+      }
+      PairResult* d_items = d_out ? d_out : d_item_results;
+      PEAQ_CUDA(launch_seg_gather_results(d_res, seg_table.first_vp, n_out, d_items, stream));
+      launches++;
+      d_res = d_items;
+      if (h_redo)
+        PEAQ_CUDA(cudaMemcpyAsync(h_redo, d_seg_redo, (size_t)n_out, cudaMemcpyDeviceToHost, stream));
+    }
     if (!blocking) return 0;
     if (h_out) {
-      PEAQ_CUDA(cudaMemcpyAsync(h_out, d_res, n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost, stream));
+      PEAQ_CUDA(cudaMemcpyAsync(h_out, d_res, n_out * sizeof(PairResult), cudaMemcpyDeviceToHost, stream));
     }
     return finish_batch();
+  }
+
+  // how many segments an item of n samples is cut into, and their length (a function of n alone,
+  // so that an item's result does not depend on the batch it is part of)
+  static unsigned segments_for_samples(uint64_t n, uint64_t* seg_len) {
+    uint64_t len = kSegSamples;
+    uint64_t k = std::max<uint64_t>(1, (n + len / 2) / len);
+    if (k > 512) {   // seg_combine_* handle 512 segments per item
+      len *= (k + 511) / 512;
+      k = std::max<uint64_t>(1, (n + len / 2) / len);
+    }
+    *seg_len = len;
+    return (unsigned)k;
+  }
+
+  // A fresh batch of whole items, PCM resident on the device: items long enough are cut into
+  // segments (peaq_segments.cu), the others run as they are.  h_redo (n_items bytes, may be filled
+  // asynchronously like h_out): items whose segments' assumptions did not hold; the caller runs
+  // them again with segments = false.
+  int process_items(const float* d_ref, const float* d_test, size_t pair_stride, int n_items, int C,
+                    const uint64_t* ns, const unsigned* nf, const unsigned* nfb, PairResult* h_out,
+                    PairResult* d_out, bool blocking, unsigned char* h_redo, bool segments = true) {
+    bool any = false;
+    if (segments && segment_mode && !keep_records) {
+      uint64_t len;
+      for (int i = 0; i < n_items && !any; i++) any = segments_for_samples(ns[i], &len) > 1;
+    }
+    if (!any) {
+      if (h_redo) std::memset(h_redo, 0, (size_t)n_items);
+      const ClockPlan fft{ns, ns, nf}, fb{ns, ns, nfb};
+      return process_resident(d_ref, d_test, pair_stride, n_items, C, fft, fb, true, h_out, d_out, blocking);
+    }
+    SegPlan sp;
+    sp.n_items = n_items;
+    std::vector<uint64_t> v_ns_fft, v_ns_fb;
+    std::vector<unsigned> v_nf, v_nfb;
+    for (int i = 0; i < n_items; i++) {
+      uint64_t len;
+      const unsigned k_seg = segments_for_samples(ns[i], &len);
+      sp.first_vp.push_back((unsigned)sp.base.size());
+      sp.n_seg.push_back(k_seg);
+      for (unsigned k = 0; k < k_seg; k++) {
+        const uint64_t a = (uint64_t)k * len, w = k ? a - kSegWarmSamples : 0;   // owned from a, run from w
+        const bool last = k + 1 == k_seg;
+        sp.base.push_back((unsigned long long)i * pair_stride + w * C);
+        sp.seg_index.push_back(k);
+        sp.frame0_fft.push_back((unsigned)(w / kFftStep));
+        sp.acc_start_fft.push_back((unsigned)(a / kFftStep));
+        sp.frame0_fb.push_back((unsigned)(w / kFbFrame));
+        sp.acc_start_fb.push_back((unsigned)(a / kFbFrame));
+        if (last) {
+          v_ns_fft.push_back(ns[i] - w);
+          v_ns_fb.push_back(ns[i] - w);
+          v_nf.push_back(nf[i] - (unsigned)(w / kFftStep));
+          v_nfb.push_back(nfb[i] - (unsigned)(w / kFbFrame));
+        } else {
+          const uint64_t span = a + len - w;   // multiples of both frame steps
+          v_ns_fft.push_back(span + (kFftFrame - kFftStep));   // the last frame's second half
+          v_ns_fb.push_back(span);
+          v_nf.push_back((unsigned)(span / kFftStep));
+          v_nfb.push_back((unsigned)(span / kFbFrame));
+        }
+      }
+    }
+    const int n_vp = (int)sp.base.size();
+    const ClockPlan fft{v_ns_fft.data(), v_ns_fft.data(), v_nf.data()}, fb{v_ns_fb.data(), v_ns_fb.data(), v_nfb.data()};
+    return process_resident(d_ref, d_test, pair_stride, n_vp, C, fft, fb, true, h_out, d_out, blocking, nullptr, nullptr,
+                            0, &sp, h_redo);
   }
 
   int finish_batch() {
@@ -749,10 +910,17 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
   PEAQ_CUDA(cudaEventRecord(t0.ev, e->stream));
 
   PairResult* res = reinterpret_cast<PairResult*>(out);
+  std::vector<unsigned char> redo((size_t)n_pairs, 0);   // items whose segments must be run again whole
   if (b->on_device) {
-    const Engine::ClockPlan fft{ns.data(), ns.data(), nf.data()}, fb{ns.data(), ns.data(), nfb.data()};
-    rc = e->process_resident(b->ref, b->test, b->pair_stride, n_pairs, C, fft, fb, true, res);
+    rc = e->process_items(b->ref, b->test, b->pair_stride, n_pairs, C, ns.data(), nf.data(), nfb.data(), res, nullptr,
+                          true, redo.data());
     if (rc) return rc;
+    for (int p = 0; p < n_pairs; p++) {
+      if (!redo[p]) continue;
+      rc = e->process_items(b->ref + (size_t)p * b->pair_stride, b->test + (size_t)p * b->pair_stride, b->pair_stride,
+                            1, C, &ns[p], &nf[p], &nfb[p], res + p, nullptr, true, nullptr, false);
+      if (rc) return rc;
+    }
   } else {
     // host input: sub-batches of pairs are staged through two device slots; the
     // H2D copy of sub-batch i+1 (copy stream) overlaps the kernels of sub-batch i
@@ -783,7 +951,15 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     // size everything once, for the largest sub-batch: growing later would free memory under
     // queued kernels (cudaFree synchronises the device and stalls the copy / compute overlap)
     {
-      const int np_max = *std::max_element(sizes.begin(), sizes.end());
+      int np_max = 0;   // in virtual pairs: long items count once per segment
+      for (int i = 0, q0 = 0; i < (int)sizes.size(); q0 += sizes[i], i++) {
+        int n_vp = 0;
+        for (int q = q0; q < q0 + sizes[i]; q++) {
+          uint64_t len;
+          n_vp += e->segment_mode && !e->keep_records ? (int)Engine::segments_for_samples(ns[q], &len) : 1;
+        }
+        np_max = std::max(np_max, n_vp);
+      }
       const StateLayout S = make_state_layout(C, e->h_tables->fft_bands);
       const AdvStateLayout A = make_adv_state_layout(C);
       if ((rc = e->ensure_pairs((size_t)np_max, e->advanced ? (size_t)A.stride : (size_t)S.stride, false))) return rc;
@@ -813,16 +989,26 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
       }
       PEAQ_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
       PEAQ_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
-      const Engine::ClockPlan fft{ns.data() + p0, ns.data() + p0, nf.data() + p0},
-          fb{ns.data() + p0, ns.data() + p0, nfb.data() + p0};
-      rc = e->process_resident(e->d_stage[slot][0], e->d_stage[slot][1], stride, np, C, fft, fb, true, nullptr,
-                               d_all + p0, false);
+      rc = e->process_items(e->d_stage[slot][0], e->d_stage[slot][1], stride, np, C, ns.data() + p0, nf.data() + p0,
+                            nfb.data() + p0, nullptr, d_all + p0, false, redo.data() + p0);
       if (rc) return rc;
       PEAQ_CUDA(cudaEventRecord(e->ev_freed[slot], e->stream));
     }
     PEAQ_CUDA(cudaMemcpyAsync(res, d_all, (size_t)n_pairs * sizeof(PairResult), cudaMemcpyDeviceToHost, e->stream));
     rc = e->finish_batch();
     if (rc) return rc;
+    for (int p = 0; p < n_pairs; p++) {
+      if (!redo[p]) continue;
+      // (rare: an item whose first half minute is silent) staged again and run as a whole
+      const size_t floats = (size_t)ns[p] * C;
+      PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[0][0], b->ref + (size_t)p * stride, floats * sizeof(float),
+                                cudaMemcpyHostToDevice, e->stream));
+      PEAQ_CUDA(cudaMemcpyAsync(e->d_stage[0][1], b->test + (size_t)p * stride, floats * sizeof(float),
+                                cudaMemcpyHostToDevice, e->stream));
+      rc = e->process_items(e->d_stage[0][0], e->d_stage[0][1], stride, 1, C, &ns[p], &nf[p], &nfb[p], res + p, nullptr,
+                            true, nullptr, false);
+      if (rc) return rc;
+    }
   }
   PEAQ_CUDA(cudaEventRecord(t1.ev, e->stream));
   PEAQ_CUDA(cudaEventSynchronize(t1.ev));

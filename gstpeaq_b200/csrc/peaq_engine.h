@@ -56,9 +56,17 @@ struct StateLayout {
   int off_band;    // [field][c][b], kBandStateFields fields
   int off_acc;     // [c][kNumAcc][kAccFields]
   int off_scalar;  // signal energy, noise energy
-  int off_ints;    // int32: status, frame counter, loudness-reached frame, fb frame counter, fb status
+  int off_ints;    // int32: status, frame counter, loudness-reached frame, spare | segment words (kSeg*)
   int stride;
 };
+
+// Segment words of the basic state (int32 slots after the three counters; zero for whole items,
+// see peaq_segments.cu): first frame whose contributions count, "an owned frame was above the
+// threshold", 1 + first frame above the threshold (0: none yet)
+constexpr int kSegAccStart = 4, kSegOwnedAbove = 5, kSegFirstAbove = 6;
+// the same for the two clocks of the advanced state
+constexpr int kASegAccStartFft = 5, kASegAccStartFb = 6, kASegOwnedAboveFft = 7, kASegOwnedAboveFb = 8,
+              kASegFirstAboveFft = 9, kASegFirstAboveFb = 10;
 
 inline StateLayout make_state_layout(int C, int B) {
   StateLayout S;
@@ -83,7 +91,7 @@ struct AdvStateLayout {
   int off_fb_mod;         // [c][ref|test][3][40]
   int off_fb_acc;         // [c][3][kAccFields] RmsModDiff, RmsNoiseLoudAsym, AvgLinDist
   int off_fb_movs;        // 3 channel-averaged MOV values published by the fb scan
-  int off_ints;           // int32: fft status, fft frames, fb status, fb frames, loudness frame, (unused)
+  int off_ints;           // int32: fft status, fft frames, fb status, fb frames, loudness frame | segment words (kASeg*)
   int stride;
 };
 
@@ -99,7 +107,7 @@ inline AdvStateLayout make_adv_state_layout(int C) {
   S.off_fb_acc = S.off_fb_mod + C * 2 * 3 * kFbBands;
   S.off_fb_movs = S.off_fb_acc + C * 3 * kAccFields;
   S.off_ints = S.off_fb_movs + 3;
-  S.stride = S.off_ints + 4;
+  S.stride = S.off_ints + 6;
   return S;
 }
 
@@ -125,7 +133,14 @@ struct PcmView {
   const unsigned long long* n_samples_test;  // device, per pair: length of the test signal
   const unsigned* n_frames;                  // device, per pair: frames of this clock to run
   int channels;
+  // device, per pair, or null: where the pair's signals start, in floats from ref / test (segments
+  // of long items are windows into their item); null: pair * pair_stride
+  const unsigned long long* base = nullptr;
 };
+
+__host__ __device__ inline size_t pcm_pair_offset(const PcmView& pcm, int pair) {
+  return pcm.base ? (size_t)pcm.base[pair] : (size_t)pair * pcm.pair_stride;
+}
 
 struct LaunchStats {
   unsigned long long launches;
@@ -180,5 +195,27 @@ cudaError_t launch_adv_fft_scan(const DeviceTables* d_tables, const double* reco
                                 const unsigned* n_frames, unsigned first_frame, unsigned n_chunk_frames,
                                 double* state, AdvStateLayout S, PairResult* results, int n_pairs,
                                 cudaStream_t stream);
+
+// ---- segments of long items (peaq_segments.cu) -------------------------------------------------
+constexpr unsigned long long kSegWarmSamples = 196608;          // 4.096 s = 192 FFT-clock frames = 1024 filter-bank frames
+constexpr unsigned long long kSegSamples = 8 * kSegWarmSamples;   // 32.8 s = 1536 / 8192 frames; multiples of the DC-reject scan's blocks
+
+// device arrays describing the virtual pairs (one per segment) of a batch and their items
+struct SegTable {
+  const int* seg_index;            // [vp] 0 for an item's first segment
+  const unsigned* frame0_fft;      // [vp] absolute index of the first frame the vp runs (its warm-up start)
+  const unsigned* acc_start_fft;   // [vp] absolute index of the first frame the vp owns
+  const unsigned* frame0_fb;
+  const unsigned* acc_start_fb;
+  const int* first_vp;             // [item]
+  const int* n_seg;                // [item]
+};
+cudaError_t launch_seg_init(double* state, const StateLayout* S, const AdvStateLayout* A, int n_vp,
+                            const SegTable& t, cudaStream_t stream);
+// sums of the segments -> segment 0's state block; redo[item] = 1 when the item must be run as a whole
+cudaError_t launch_seg_combine(double* state, const StateLayout* S, const AdvStateLayout* A, int n_items,
+                               const SegTable& t, unsigned char* redo, cudaStream_t stream);
+cudaError_t launch_seg_gather_results(const PairResult* res, const int* first_vp, int n_items, PairResult* out,
+                                      cudaStream_t stream);
 
 }  // namespace peaq

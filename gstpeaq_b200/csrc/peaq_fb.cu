@@ -54,7 +54,7 @@ __global__ void fb_flags_kernel(PcmView pcm, unsigned first_frame, unsigned n_ch
   if (frame < pcm.n_frames[pair]) {
     const int C = pcm.channels;
     const unsigned long long n = pcm.n_samples[pair];
-    const float* __restrict__ sig = pcm.ref + (size_t)pair * pcm.pair_stride;
+    const float* __restrict__ sig = pcm.ref + pcm_pair_offset(pcm, pair);
     const unsigned long long s0 = (unsigned long long)frame * kFbFrame;
     for (int c = 0; c < C && !above; c++) {
       // literal replay: float running sum, double increments (gstpeaq.c:1088-1096)
@@ -174,7 +174,7 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
   if (stream >= n_streams) return;
   const int pair = stream / (2 * C), c = (stream >> 1) % C, side = stream & 1;
   const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
-  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
+  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + pcm_pair_offset(pcm, pair);
   const bool aligned = (reinterpret_cast<uintptr_t>(sig) & 15) == 0;
   double* out = hp + (size_t)stream * hp_stride;
   double* st = hp_state + (size_t)stream * kHpStateDoubles;
@@ -294,7 +294,7 @@ __global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmVi
   const int stream = (int)(idx / n_blocks), blk = (int)(idx - (long long)stream * n_blocks);
   const int pair = stream / (2 * C), c = (stream >> 1) % C, side = stream & 1;
   const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
-  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + (size_t)pair * pcm.pair_stride;
+  const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + pcm_pair_offset(pcm, pair);
   const double lf = T->level_factor_fb;
   const unsigned b0 = (unsigned)blk * kHpL;
   const unsigned len = min((unsigned)kHpL, chunk_samples - b0);
@@ -746,8 +746,12 @@ cudaError_t launch_fb_flags(PcmView pcm, int n_pairs, unsigned first_frame, unsi
   for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
     const int np = n_pairs - p0 < 65535 ? n_pairs - p0 : 65535;
     PcmView v = pcm;
-    v.ref += (size_t)p0 * pcm.pair_stride;
-    v.test += (size_t)p0 * pcm.pair_stride;
+    if (pcm.base) {
+      v.base += p0;
+    } else {
+      v.ref += (size_t)p0 * pcm.pair_stride;
+      v.test += (size_t)p0 * pcm.pair_stride;
+    }
     v.n_samples += p0;
     v.n_samples_test += p0;
     v.n_frames += p0;

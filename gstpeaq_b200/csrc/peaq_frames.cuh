@@ -497,8 +497,8 @@ __device__ __forceinline__ void frame_load_twiddles(const DeviceTables* __restri
 // (last, zero-padded frame; odd strides) frame_body fills the same buffers with a guarded copy.
 __device__ __forceinline__ bool frame_tma_ok(const PcmView& pcm, int pair, unsigned frame) {
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
-  const float* ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
-  const float* test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  const float* ref_sig = pcm.ref + pcm_pair_offset(pcm, pair);
+  const float* test_sig = pcm.test + pcm_pair_offset(pcm, pair);
   return (reinterpret_cast<uintptr_t>(ref_sig) & 15) == 0 && (reinterpret_cast<uintptr_t>(test_sig) & 15) == 0 &&
          s0 + kFftFrame <= pcm.n_samples[pair] && s0 + kFftFrame <= pcm.n_samples_test[pair];
 }
@@ -508,8 +508,8 @@ __device__ __forceinline__ void frame_tma_issue(const PcmView& pcm, int pair, un
   const int C = pcm.channels;
   FrameMail* mail = frame_mail(smem, C);
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
-  const float* ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
-  const float* test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  const float* ref_sig = pcm.ref + pcm_pair_offset(pcm, pair);
+  const float* test_sig = pcm.test + pcm_pair_offset(pcm, pair);
   const unsigned bytes = kFftFrame * C * sizeof(float);
   mbar_expect_tx(&mail->mbar, 2 * bytes);
   tma_load_1d(frame_stream_buf(smem, 0), ref_sig + s0 * C, bytes, &mail->mbar);
@@ -549,8 +549,8 @@ __device__ __forceinline__ void frame_body(const DeviceTables* __restrict__ T, c
 
   const unsigned long long n_ref = pcm.n_samples[pair], n_test = pcm.n_samples_test[pair];
   const unsigned long long s0 = (unsigned long long)frame * kFftStep;
-  const float* __restrict__ ref_sig = pcm.ref + (size_t)pair * pcm.pair_stride;
-  const float* __restrict__ test_sig = pcm.test + (size_t)pair * pcm.pair_stride;
+  const float* __restrict__ ref_sig = pcm.ref + pcm_pair_offset(pcm, pair);
+  const float* __restrict__ test_sig = pcm.test + pcm_pair_offset(pcm, pair);
   float* raw_ref = reinterpret_cast<float*>(frame_stream_buf(smem, 0));
   float* raw_test = reinterpret_cast<float*>(frame_stream_buf(smem, 1));
   if (!tma_ok) {

@@ -183,6 +183,11 @@ struct ScanCounters {
   int status;
   unsigned frame_counter, loud_frame;
   double sig_energy, noise_energy;
+  // segments of long items (peaq_segments.cu; all zero for whole items): sums restart at frame
+  // acc_start (the frames before it only warm the recurrences up), `owned_above`: a frame from
+  // acc_start on was above the threshold, first_above: 1 + the first frame above it (0: none)
+  unsigned acc_start, first_above;
+  int owned_above;
 };
 
 // thread identity inside the scan CTA
@@ -468,8 +473,14 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   if (loud_frame == UINT_MAX && latch_sh) loud_frame = frame_counter;
 
   // ---- accumulators: thread (c, k) owns slot k of channel c -------------------
+  const bool seg_start = frame_counter == cnt.acc_start;   // (frame 0 of a whole item: everything is zero anyway)
   if (acc_thread) {
     acc_io.load(acc);
+    if (seg_start) {
+      // the sums restart, histories (window, filter state) carry over from the warm-up frames
+      acc.num = acc.den = acc.snum = acc.sden = acc.smax = 0.;
+      if (acc_mode == kModeFilteredMax) acc.x0 = 0.;
+    }
     // peaq_movaccum_set_tentative (movaccum.c:317-354) for every slot
     int st_new = status;
     if (!above) {
@@ -551,6 +562,11 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   } else {
     status = kStNormal;
   }
+  if (seg_start) cnt.sig_energy = cnt.noise_energy = 0.;
+  if (above) {
+    if (cnt.first_above == 0) cnt.first_above = frame_counter + 1;
+    if (frame_counter >= cnt.acc_start) cnt.owned_above = 1;
+  }
   cnt.sig_energy += in.snr[0];
   cnt.noise_energy += in.snr[1];
   frame_counter++;
@@ -612,6 +628,9 @@ __device__ __forceinline__ void load_counters(ScanCounters& cnt, const double* s
   cnt.status = st_ints[0];
   cnt.frame_counter = (unsigned)st_ints[1];
   cnt.loud_frame = (unsigned)st_ints[2];
+  cnt.acc_start = (unsigned)st_ints[kSegAccStart];
+  cnt.owned_above = st_ints[kSegOwnedAbove];
+  cnt.first_above = (unsigned)st_ints[kSegFirstAbove];
   cnt.sig_energy = st[S.off_scalar];
   cnt.noise_energy = st[S.off_scalar + 1];
 }
@@ -620,6 +639,8 @@ __device__ __forceinline__ void store_counters(const ScanCounters& cnt, double* 
   st_ints[0] = cnt.status;
   st_ints[1] = (int)cnt.frame_counter;
   st_ints[2] = (int)cnt.loud_frame;
+  st_ints[kSegOwnedAbove] = cnt.owned_above;
+  st_ints[kSegFirstAbove] = (int)cnt.first_above;
   st[S.off_scalar] = cnt.sig_energy;
   st[S.off_scalar + 1] = cnt.noise_energy;
 }

@@ -230,6 +230,10 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
   int status = st_ints[2];
   unsigned frame_counter = (unsigned)st_ints[3];
   unsigned loud_frame = (unsigned)st_ints[4];
+  // segments of long items (peaq_segments.cu; zero for whole items)
+  const unsigned acc_start = (unsigned)st_ints[kASegAccStartFb];
+  int owned_above = st_ints[kASegOwnedAboveFb];
+  unsigned first_above = (unsigned)st_ints[kASegFirstAboveFb];
   __syncthreads();
 
   const double deriv_factor = (double)48000 / kFbFrame;
@@ -449,6 +453,9 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
     if (side == 0 && lane == 0) {
       const double s_mc = sm.tsum[chan][0], s_ld = sm.tsum[chan][1];
       double (*a)[kAccFields] = sm.acc[chan];
+      if (frame_counter == acc_start) {   // a segment's sums restart after its warm-up frames
+        for (int k = 0; k < 3; k++) a[k][0] = a[k][1] = a[k][2] = a[k][5] = a[k][6] = a[k][7] = 0.;
+      }
       // peaq_movaccum_set_tentative on the three fb-clock accumulators (gstpeaq.c:974-979)
       int st_new = status;
       if (!above) {
@@ -504,6 +511,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
       if (status == kStNormal) status = kStTentative;
     } else {
       status = kStNormal;
+      if (first_above == 0) first_above = frame_counter + 1;
+      if (frame_counter >= acc_start) owned_above = 1;
     }
     frame_counter++;
     // no barrier here: everything the next frame overwrites before its first barrier was last
@@ -534,6 +543,8 @@ fb_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ en
     st_ints[2] = status;
     st_ints[3] = (int)frame_counter;
     st_ints[4] = (int)loud_frame;
+    st_ints[kASegOwnedAboveFb] = owned_above;
+    st_ints[kASegFirstAboveFb] = (int)first_above;
     // peaq_movaccum_get_value (movaccum.c:438-481), averaged over channels
     const bool tent = status == kStTentative;
     double v0 = 0., v1 = 0., v2 = 0.;
@@ -583,6 +594,9 @@ adv_fft_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict
   }
   int status = st_ints[0];
   unsigned frame_counter = (unsigned)st_ints[1];
+  const unsigned acc_start = (unsigned)st_ints[kASegAccStartFft];   // segments of long items (peaq_segments.cu)
+  int owned_above = st_ints[kASegOwnedAboveFft];
+  unsigned first_above = (unsigned)st_ints[kASegFirstAboveFft];
   double sig_energy = st[S.off_fft_scalar], noise_energy = st[S.off_fft_scalar + 1];
   const double a_ear = T->fft.a_ear[bb], maskdiff = T->maskdiff[bb];
 
@@ -601,6 +615,11 @@ adv_fft_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict
     curr = warp_sum(curr);
     if (lane == 0) red[par][c][wig] = curr;
     __syncthreads();
+    const bool seg_start = frame_counter == acc_start;
+    if (seg_start) {   // a segment's sums restart after its warm-up frames
+      num = den = snum = sden = 0.;
+      sig_energy = noise_energy = 0.;
+    }
     if (acc_thread) {
       if (!above) {
         if (status == kStNormal) {
@@ -624,6 +643,8 @@ adv_fft_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict
       if (status == kStNormal) status = kStTentative;
     } else {
       status = kStNormal;
+      if (first_above == 0) first_above = frame_counter + 1;
+      if (frame_counter >= acc_start) owned_above = 1;
     }
     sig_energy += rec[L.off_snr];
     noise_energy += rec[L.off_snr + 1];
@@ -641,6 +662,8 @@ adv_fft_scan_kernel(const DeviceTables* __restrict__ T, const double* __restrict
   if (threadIdx.x == 0) {
     st_ints[0] = status;
     st_ints[1] = (int)frame_counter;
+    st_ints[kASegOwnedAboveFft] = owned_above;
+    st_ints[kASegFirstAboveFft] = (int)first_above;
     st[S.off_fft_scalar] = sig_energy;
     st[S.off_fft_scalar + 1] = noise_energy;
     double movs[5];

@@ -8,14 +8,14 @@ import gstpeaq_b200 as G
 def main():
     n_pairs = int(os.environ.get("PEAQ_PROFILE_PAIRS", "592"))
     advanced = int(os.environ.get("PEAQ_PROFILE_ADVANCED", "0"))
-    ns, ch = 480000, 2
+    ns, ch = 48000 * int(os.environ.get("PEAQ_PROFILE_SECONDS", "10")), 2
     L = G.load_library()
     eng = G.Engine(0, advanced=bool(advanced))
     dref = G.DeviceBuffer(0, n_pairs * ns * ch * 4); dtest = G.DeviceBuffer(0, n_pairs * ns * ch * 4)
     G._check(L.peaq_b200_synth_pairs(0, dref.ptr, dtest.ptr, ns * ch, n_pairs, 0, ns, ch))
     for _ in range(3):
         out = eng.run_device(dref.ptr, dtest.ptr, n_pairs, ns * ch, ch, ns)
-        print("ms total %.2f frames %.2f scan %.2f" % (eng.last_ms(0), eng.last_ms(1), eng.last_ms(2)))
+        print("ms total %.2f frames %.2f scan %.2f fb-all %.2f bank %.2f spread+scan %.2f" % tuple(eng.last_ms(k) for k in (0, 1, 2, 4, 5, 6)))
 
 if __name__ == "__main__":
     main()

@@ -783,3 +783,83 @@ def test_pipelined_chunks_are_bit_identical_to_the_serial_loop(monkeypatch):
     assert a.tobytes() == b.tobytes() and a2.tobytes() == b.tobytes()
     want = H.oracle_run_pair(ref[2, :lengths[2] * ch], test[2, :lengths[2] * ch], ch)
     check_result(a[2], want, "pipelined pair 2")
+
+
+# ---------------------------------------------------------------------------
+# long items as segments (peaq_segments.cu; BASELINE configs[4])
+
+def _run_one(monkeypatch, advanced, ref, test, ch, ns=None, **env):
+    e = _engine_with_env(monkeypatch, advanced=advanced, **env)
+    try:
+        return e.run_host(ref, test, ch, n_samples=ns)
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_segmented_long_items_match_oracle_and_the_whole_run(monkeypatch, advanced):
+    """Items longer than 49 s run as ~33 s segments with a 4.1 s warm-up each.  A ragged batch --
+    100 s (3 segments), 75 s with a silent stretch across the first segment boundary and a silent
+    tail (TENTATIVE accumulators across segments), 20 s (not cut) -- against the oracle, and
+    against the same engine with segments switched off: MOVs to 1e-9 (observed <= 1e-13; the
+    warm-up leaves the recurrences within an ulp or two of the sequential run)."""
+    ch = 2
+    lengths = [48000 * 100, 48000 * 75, 48000 * 20]
+    stride = max(lengths) * ch
+    ref = np.zeros((3, stride), np.float32)
+    test = np.zeros_like(ref)
+    r, t = synth_pair(900, lengths[0], ch)
+    ref[0, :r.size] = r
+    test[0, :t.size] = t
+    x, y = noise_pair(11, lengths[1], ch, tail=48000 * 9)
+    x[ch * 48000 * 30:ch * 48000 * 36] = 0      # silence over the boundary at 32.8 s
+    y[ch * 48000 * 30:ch * 48000 * 36] = 0
+    ref[1, :x.size] = x
+    test[1, :y.size] = y
+    r, t = synth_pair(901, lengths[2], ch)
+    ref[2, :r.size] = r
+    test[2, :t.size] = t
+    ns = np.array(lengths, np.uint64)
+    seg = _run_one(monkeypatch, advanced, ref, test, ch, ns, PEAQ_B200_SEGMENTS="1")
+    whole = _run_one(monkeypatch, advanced, ref, test, ch, ns, PEAQ_B200_SEGMENTS="0")
+    assert seg[2].tobytes() == whole[2].tobytes()          # the short item is not touched
+    n = 5 if advanced else 11
+    for p in range(3):
+        for k in ("frames_fft", "frames_fb", "loudness_reached_frame", "n_movs"):
+            assert seg[k][p] == whole[k][p], (p, k)
+        np.testing.assert_allclose(seg["movs"][p][:n], whole["movs"][p][:n], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose([seg["odg"][p], seg["di"][p], seg["totalsnr"][p]],
+                                   [whole["odg"][p], whole["di"][p], whole["totalsnr"][p]], rtol=0, atol=1e-9,
+                                   equal_nan=True)
+        want = H.oracle_run_pair(ref[p, :lengths[p] * ch], test[p, :lengths[p] * ch], ch, advanced=advanced)
+        check_result(seg[p], want, "segmented item %d adv %d" % (p, advanced))
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_segments_fall_back_to_the_whole_item_when_their_assumptions_fail(monkeypatch, advanced):
+    """An item whose first 40 s are digital silence: no frame above the threshold and no loudness
+    latch before the second segment's warm-up, so the segments' start assumptions are wrong; the
+    engine notices (redo flag of seg_combine_*) and runs the item as a whole -- same bits as
+    with segments switched off -- also as part of a batch, from device-resident PCM too."""
+    ch = 2
+    n = 48000 * 70
+    x, y = noise_pair(12, n, ch, lead=48000 * 40)
+    r, t = synth_pair(902, n, ch)
+    ref = np.stack([r, x])
+    test = np.stack([t, y])
+    seg = _run_one(monkeypatch, advanced, ref, test, ch, None, PEAQ_B200_SEGMENTS="1")
+    whole = _run_one(monkeypatch, advanced, ref, test, ch, None, PEAQ_B200_SEGMENTS="0")
+    assert seg[1].tobytes() == whole[1].tobytes()
+    want = H.oracle_run_pair(x, y, ch, advanced=advanced)
+    check_result(seg[1], want, "silent start adv %d" % advanced)
+    e = _engine_with_env(monkeypatch, advanced=advanced, PEAQ_B200_SEGMENTS="1")
+    try:
+        dr = G.DeviceBuffer(0, ref.nbytes)
+        dt = G.DeviceBuffer(0, test.nbytes)
+        L = G.load_library()
+        G._check(L.peaq_b200_memcpy_h2d(0, dr.ptr, ref.ctypes.data, ref.nbytes))
+        G._check(L.peaq_b200_memcpy_h2d(0, dt.ptr, test.ctypes.data, test.nbytes))
+        dev = e.run_device(dr.ptr, dt.ptr, 2, n * ch, ch, n)
+    finally:
+        e.close()
+    assert dev.tobytes() == seg.tobytes()
