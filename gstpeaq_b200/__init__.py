@@ -318,6 +318,22 @@ class Engine:
         movs = buf[n_exc:n_exc + n_pairs * F * channels * 8].reshape(n_pairs, F, channels, 8)
         return exc, movs
 
+    def scan_debug(self, n_pairs, channels, bands=109):
+        """Basic mode taps of the scan kernel for the last run (needs keep_records(True)):
+        (excitation [pair, frame, ref|test, channel, band], terms [pair, frame, channel, 8])"""
+        cap = 1 << 26
+        buf = np.zeros(cap, dtype=np.float64)
+        n = C.c_size_t()
+        fr = C.c_uint32()
+        _check(self.lib.peaq_b200_engine_copy_fb_debug(self.h, buf.ctypes.data, cap, C.byref(n),
+                                                       C.byref(fr)))
+        F = fr.value
+        per = 2 * channels * bands + channels * 8
+        rows = buf[:n_pairs * F * per].reshape(n_pairs, F, per)
+        exc = rows[:, :, :2 * channels * bands].reshape(n_pairs, F, 2, channels, bands)
+        terms = rows[:, :, 2 * channels * bands:].reshape(n_pairs, F, channels, 8)
+        return exc, terms
+
     def records(self, n_pairs, n_frames):
         """Per-frame records of the last run (needs keep_records(True))."""
         lay = np.zeros(9, dtype=np.int32)

@@ -586,9 +586,20 @@ struct Engine {
                  (pipeline_mode == 1 || (pipeline_mode < 0 && n_pairs < 2 * sm_count))) {
         if ((rc = run_fft_clock_pipelined(pcm, n_pairs, max_frames, L, S, d_res))) return rc;
       } else {
+        // keep_records: one chunk; K2's per-frame tap goes to the debug buffer (tests)
+        double* tap = nullptr;
+        last_fbdbg_doubles = 0;
+        if (keep_records) {
+          const size_t need = (size_t)n_pairs * std::max(max_frames, 1u) * scan_tap_doubles_per_frame(C, B);
+          if ((rc = ensure(&d_fbdbg, &fbdbg_cap, need))) return rc;
+          PEAQ_CUDA(cudaMemsetAsync(d_fbdbg, 0, need * sizeof(double), stream));
+          tap = d_fbdbg;
+          last_fbdbg_doubles = need;
+          last_fb_frames = std::max(max_frames, 1u);
+        }
         rc = run_fft_clock(pcm, n_pairs, max_frames, L, [&](unsigned first, unsigned n) {
           return launch_scan_basic(d_tables, d_records, L, pcm.n_frames, first, n, d_state, S, d_res,
-                                   n_pairs, stream);
+                                   n_pairs, stream, tap);
         });
         if (rc) return rc;
       }
@@ -701,7 +712,7 @@ struct Engine {
         // history is simply what precedes it there
         PEAQ_CUDA(launch_fb_bank(d_tables, h_tables, d_hp + (whole ? (size_t)first * kFbFrame : 0), hp_stride,
                                  n_streams, n_sub, d_fbout, d_hp_state, first == 0 && reset_state, fb_direct,
-                                 stream));
+                                 pcm_fb.n_frames, first, 2 * C, stream));
         if ((rc = timer_end())) return rc;
         if ((rc = timer_begin(6))) return rc;
         PEAQ_CUDA(launch_fb_spread(d_tables, d_fbout, n_sub, pcm_fb.n_frames, first, d_state, A, d_fbenergy,
@@ -772,12 +783,14 @@ struct Engine {
   // how many segments an item of n samples is cut into, and their length (a function of n alone,
   // so that an item's result does not depend on the batch it is part of)
   static unsigned segments_for_samples(uint64_t n, uint64_t* seg_len) {
-    uint64_t len = kSegSamples;
-    uint64_t k = std::max<uint64_t>(1, (n + len / 2) / len);
-    if (k > 512) {   // seg_combine_* handle 512 segments per item
-      len *= (k + 511) / 512;
-      k = std::max<uint64_t>(1, (n + len / 2) / len);
-    }
+    // about kSegSamples each, all segments of an item equally long (no ragged tail: the last
+    // segment would otherwise keep every per-stream kernel running for the others' sake),
+    // boundaries on multiples of both frame steps and of the DC-reject scan's blocks
+    const uint64_t grid = 3072;   // lcm(1024, 192), = 6 blocks of 512
+    uint64_t k = std::max<uint64_t>(1, (n + kSegSamples / 2) / kSegSamples);
+    k = std::min<uint64_t>(k, 512);   // seg_combine_* handle 512 segments per item
+    uint64_t len = ((n + k - 1) / k + grid - 1) / grid * grid;
+    while (k > 1 && (k - 1) * len >= n) k--;
     *seg_len = len;
     return (unsigned)k;
   }

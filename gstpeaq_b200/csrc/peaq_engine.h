@@ -160,7 +160,9 @@ cudaError_t launch_fft_frames(const DeviceTables* d_tables, PcmView pcm, int n_p
 cudaError_t launch_scan_basic(const DeviceTables* d_tables, const double* records, RecordLayout L,
                               const unsigned* n_frames, unsigned first_frame,
                               unsigned n_chunk_frames, double* state, StateLayout S,
-                              PairResult* results, int n_pairs, cudaStream_t stream);
+                              PairResult* results, int n_pairs, cudaStream_t stream,
+                              double* dbg = nullptr /* test tap: [pair][chunk frame][scan_tap_doubles_per_frame] */);
+int scan_tap_doubles_per_frame(int C, int B);
 
 size_t fft_frames_smem_bytes(int channels);
 
@@ -182,7 +184,8 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
                            const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
                            double* fbout, double* hp_state, bool first_chunk, bool direct_only,
-                           cudaStream_t stream);
+                           const unsigned* n_frames /* device, per pair: frames of the filter-bank clock */,
+                           unsigned first_frame, int streams_per_pair, cudaStream_t stream);
 cudaError_t launch_init_adv_state(double* state, AdvStateLayout S, int n_pairs, cudaStream_t stream);
 cudaError_t launch_fb_spread(const DeviceTables* d_tables, const double* fbout, unsigned n_sub,
                              const unsigned* n_frames, unsigned first_frame, double* state,

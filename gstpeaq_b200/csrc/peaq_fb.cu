@@ -283,52 +283,127 @@ __global__ void fb_hp_kernel(const DeviceTables* __restrict__ T, PcmView pcm, in
 // starts (= s0) -> ends; MODE 2: output pass from starts (= s0 + d).  The last block may be
 // partial (end of the chunk): its recurrences stop exactly at the chunk's end and their running
 // states go to the stream's state header, like fb_hp_kernel leaves them.
+// One CTA = 32 consecutive blocks of one signal (pair, side): lane = block, warp = channel.  The
+// blocks' samples lie 2 KB (4 KB stereo) apart, so the PCM goes through shared memory: every
+// sub-step the CTA copies the next 32 samples of its 32 blocks with 128-bit loads (16 lanes cover
+// one block's 256-byte run), transposed into rows of odd pitch that the recurrences then read
+// without bank conflicts; the output pass hands its results back the same way (rows of 32 doubles
+// per block and channel, written out as 256-byte runs).
+constexpr int kHpTileBlocks = 32;   // blocks per CTA
+constexpr int kHpSub = 32;          // samples per sub-step
+
 template <int C, int MODE>
-__global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_streams, int n_blocks,
-                                       unsigned long long t0, unsigned chunk_samples,
-                                       double* __restrict__ hp, size_t hp_stride,
-                                       double* __restrict__ hp_state, const double* __restrict__ starts,
-                                       double* __restrict__ ends, int first_chunk) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n_streams * n_blocks) return;
-  const int stream = (int)(idx / n_blocks), blk = (int)(idx - (long long)stream * n_blocks);
-  const int pair = stream / (2 * C), c = (stream >> 1) % C, side = stream & 1;
+__global__ void __launch_bounds__(32 * C)
+fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmView pcm, int n_blocks,
+                       unsigned long long t0, unsigned chunk_samples,
+                       double* __restrict__ hp, size_t hp_stride,
+                       double* __restrict__ hp_state, const double* __restrict__ starts,
+                       double* __restrict__ ends, int first_chunk) {
+  constexpr int kPitch = kHpSub * C + 1;                 // floats per block row
+  constexpr int kVecPerBlock = kHpSub * C / 4;           // float4 per block and sub-step
+  constexpr int kVecPerThread = kHpTileBlocks * kVecPerBlock / (32 * C);   // = 8
+  __shared__ float in_s[2][kHpTileBlocks * kPitch];
+  __shared__ double out_s[MODE == 2 ? C * kHpTileBlocks * (kHpSub + 1) : 1];
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  const int pair = blockIdx.x >> 1, side = blockIdx.x & 1;
+  const int stream = pair * 2 * C + 2 * c + side;
+  const int blk0 = blockIdx.y * kHpTileBlocks;
+  const int blk = blk0 + lane;
+  const bool have = blk < n_blocks;
   const unsigned long long n = side ? pcm.n_samples_test[pair] : pcm.n_samples[pair];
   const float* __restrict__ sig = (side ? pcm.test : pcm.ref) + pcm_pair_offset(pcm, pair);
+  const bool aligned = (reinterpret_cast<uintptr_t>(sig + t0 * C) & 15) == 0;
   const double lf = T->level_factor_fb;
   const unsigned b0 = (unsigned)blk * kHpL;
-  const unsigned len = min((unsigned)kHpL, chunk_samples - b0);
+  const unsigned len = have ? min((unsigned)kHpL, chunk_samples - b0) : 0u;   // a multiple of 64 (whole frames)
+  // the longest block of the tile decides how many sub-steps the CTA runs
+  const unsigned tile_b0 = (unsigned)blk0 * kHpL;
+  const unsigned tile_len = min((unsigned)kHpL, chunk_samples - tile_b0);
   double* st = hp_state + (size_t)stream * kHpStateDoubles;
   Biquads f = Biquads{0, 0, 0, 0, 0, 0};
-  if (blk == 0) {
-    if (!first_chunk) {
-      f.x1 = st[0];
-      f.x2 = st[1];
+  if (have) {
+    if (blk == 0) {
+      if (!first_chunk) {
+        f.x1 = st[0];
+        f.x2 = st[1];
+      }
+    } else {
+      const unsigned long long s1 = t0 + b0 - 1, s2 = t0 + b0 - 2;
+      f.x1 = (s1 < n ? __ldg(sig + s1 * C + c) : 0.f) * lf;
+      f.x2 = (s2 < n ? __ldg(sig + s2 * C + c) : 0.f) * lf;
     }
-  } else {
-    const unsigned long long s1 = t0 + b0 - 1, s2 = t0 + b0 - 2;
-    f.x1 = (s1 < n ? __ldg(sig + s1 * C + c) : 0.f) * lf;
-    f.x2 = (s2 < n ? __ldg(sig + s2 * C + c) : 0.f) * lf;
+    if (MODE != 0) {
+      const double* bs = starts + ((size_t)stream * (n_blocks + 1) + blk) * 4;
+      f.y1a = bs[0]; f.y2a = bs[1]; f.y1b = bs[2]; f.y2b = bs[3];
+    }
   }
-  if (MODE != 0) {
-    const double* bs = starts + ((size_t)stream * (n_blocks + 1) + blk) * 4;
-    f.y1a = bs[0]; f.y2a = bs[1]; f.y1b = bs[2]; f.y2b = bs[3];
-  }
-  double* out = hp + (size_t)stream * hp_stride + kFbHist + b0;
-  for (unsigned i0 = 0; i0 < len; i0 += kHpBlock) {   // len is a multiple of 16 (whole frames)
-    double y[kHpBlock];
+  // the CTA's copy of sub-step i0: float4 q of the tile = block q / kVecPerBlock, offset q % kVecPerBlock
+  float4 stage[kVecPerThread];
+  auto fetch = [&](unsigned i0) {
 #pragma unroll
-    for (int k = 0; k < kHpBlock; k++) {
-      const unsigned long long s = t0 + b0 + i0 + k;
-      const float x = s < n ? __ldg(sig + s * C + c) : 0.f;
-      y[k] = f.step(x * lf);   // fbearmodel.c:289
+    for (int k = 0; k < kVecPerThread; k++) {
+      const int q = threadIdx.x + k * 32 * C;
+      const int j = q / kVecPerBlock, w = q - j * kVecPerBlock;
+      const unsigned jb0 = (unsigned)(blk0 + j) * kHpL;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (blk0 + j < n_blocks && jb0 + i0 < chunk_samples) {
+        const unsigned long long e0 = (t0 + jb0 + i0) * C + 4 * w;   // first float of the vector, from sig
+        if (aligned && e0 + 4 <= n * C) {
+          v = __ldg(reinterpret_cast<const float4*>(sig + e0));
+        } else {
+          v.x = e0 < n * C ? __ldg(sig + e0) : 0.f;
+          v.y = e0 + 1 < n * C ? __ldg(sig + e0 + 1) : 0.f;
+          v.z = e0 + 2 < n * C ? __ldg(sig + e0 + 2) : 0.f;
+          v.w = e0 + 3 < n * C ? __ldg(sig + e0 + 3) : 0.f;
+        }
+      }
+      stage[k] = v;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; k++) {
+      const int q = threadIdx.x + k * 32 * C;
+      const int j = q / kVecPerBlock, w = q - j * kVecPerBlock;
+      float* d = &in_s[buf][j * kPitch + 4 * w];
+      d[0] = stage[k].x; d[1] = stage[k].y; d[2] = stage[k].z; d[3] = stage[k].w;
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (unsigned i0 = 0; i0 < tile_len; i0 += kHpSub) {
+    const bool more = i0 + kHpSub < tile_len;
+    if (more) fetch(i0 + kHpSub);
+    if (i0 < len) {
+      const float* x = &in_s[buf][lane * kPitch + c];
+      double* y = MODE == 2 ? &out_s[(c * kHpTileBlocks + lane) * (kHpSub + 1)] : nullptr;
+#pragma unroll 8
+      for (int k = 0; k < kHpSub; k++) {
+        const double v = f.step(x[k * C] * lf);   // fbearmodel.c:289
+        if (MODE == 2) y[k] = v;
+      }
     }
     if (MODE == 2) {
-      double2* o = reinterpret_cast<double2*>(out + i0);
-#pragma unroll
-      for (int k = 0; k < kHpBlock / 2; k++) o[k] = make_double2(y[2 * k], y[2 * k + 1]);
+      __syncthreads();
+      // rows of 32 doubles per (channel, block) -> 256-byte runs of the filtered signal
+      for (int e = threadIdx.x; e < C * kHpTileBlocks * (kHpSub / 2); e += 32 * C) {
+        const int row = e / (kHpSub / 2), p2 = e - row * (kHpSub / 2);   // row = cc * 32 + j
+        const int cc = row / kHpTileBlocks, j = row - cc * kHpTileBlocks;
+        const unsigned jb0 = (unsigned)(blk0 + j) * kHpL;
+        if (blk0 + j < n_blocks && jb0 + i0 < chunk_samples) {
+          const double* r = &out_s[row * (kHpSub + 1) + 2 * p2];
+          double* out = hp + (size_t)(pair * 2 * C + 2 * cc + side) * hp_stride + kFbHist + jb0 + i0;
+          reinterpret_cast<double2*>(out)[p2] = make_double2(r[0], r[1]);
+        }
+      }
     }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
   }
+  if (!have) return;
   if (MODE != 2 && len == (unsigned)kHpL) {
     double* be = ends + ((size_t)stream * (n_blocks + 1) + blk) * 4;
     be[0] = f.y1a; be[1] = f.y2a; be[2] = f.y1b; be[3] = f.y2b;
@@ -336,7 +411,9 @@ __global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmVi
   if (blk == n_blocks - 1) {
     // running states at the end of the chunk; when the last block is full the scans have already
     // moved on to the next block and fb_hp_par_scan_kernel<1> writes the header instead
-    if (MODE == 2) { st[0] = f.x1; st[1] = f.x2; }
+    // (x[n-1], x[n-2] go to spare header slots: the CTA of block 0 may still be reading st[0..1];
+    // fb_hp_par_hist_kernel moves them afterwards)
+    if (MODE == 2) { st[22] = f.x1; st[23] = f.x2; }
     if (len < (unsigned)kHpL) {
       const int o = MODE == 2 ? 2 : (MODE == 0 ? 6 : 10);
       st[o] = f.y1a; st[o + 1] = f.y2a; st[o + 2] = f.y1b; st[o + 3] = f.y2b;
@@ -347,11 +424,21 @@ __global__ void fb_hp_par_block_kernel(const DeviceTables* __restrict__ T, PcmVi
 // MODE 0: a = zero-state end states e0[j] -> a = s0[j], j = 0..n_blocks (in place).
 // MODE 1: a = s0[j], b = e1[j] -> a = s[j] = s0[j] + d[j]; leaves (s0, d) of the block the chunk
 //         ends in -- and, if that block has not begun yet, its three start states -- in the header.
+// One WARP per stream: the recurrences over the blocks are sequential (and evaluated in exactly
+// the order fb_hp_kernel uses), but 32 blocks' inputs are read -- and their results written --
+// together, as one coalesced kilobyte; the chain runs through the warp by shuffles, every lane
+// carrying the same state and keeping the one that belongs to its block.
+__device__ __forceinline__ void hp_bcast4(const double (&v)[4], int src, double (&o)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = __shfl_sync(0xffffffffu, v[k], src);
+}
+
 template <int MODE>
 __global__ void fb_hp_par_scan_kernel(int n_streams, int n_blocks, unsigned chunk_samples,
                                       double* __restrict__ hp_state, double* __restrict__ a,
                                       const double* __restrict__ b, HpTransition M, int first_chunk) {
-  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stream = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (stream >= n_streams) return;
   double* pa = a + (size_t)stream * (n_blocks + 1) * 4;
   double* st = hp_state + (size_t)stream * kHpStateDoubles;
@@ -359,47 +446,81 @@ __global__ void fb_hp_par_scan_kernel(int n_streams, int n_blocks, unsigned chun
   if (MODE == 0) {
     double s[4] = {0., 0., 0., 0.};
     if (!first_chunk) { s[0] = st[14]; s[1] = st[15]; s[2] = st[16]; s[3] = st[17]; }
-    for (int j = 0; j <= n_full; j++) {
-      const double e[4] = {pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]};   // (j = n_full: unused)
-      pa[4 * j] = s[0]; pa[4 * j + 1] = s[1]; pa[4 * j + 2] = s[2]; pa[4 * j + 3] = s[3];
+    for (int base = 0; base <= n_full; base += 32) {
+      const int j = base + lane;
+      double e[4] = {0., 0., 0., 0.}, mine[4] = {0., 0., 0., 0.};
       if (j < n_full) {
-        double o[4];
-        hp_apply(M, s, e, o);
-        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] = pa[4 * j + k];
+      }
+      const int steps = min(32, n_full + 1 - base);
+      for (int t = 0; t < steps; t++) {
+        if (lane == t) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) mine[k] = s[k];
+        }
+        double et[4], o[4];
+        hp_bcast4(e, t, et);
+        if (base + t < n_full) {
+          hp_apply(M, s, et, o);
+#pragma unroll
+          for (int k = 0; k < 4; k++) s[k] = o[k];
+        }
+      }
+      if (j <= n_full) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) pa[4 * j + k] = mine[k];
       }
     }
   } else {
     const double* pb = b + (size_t)stream * (n_blocks + 1) * 4;
     double d[4] = {0., 0., 0., 0.};
     if (!first_chunk) { d[0] = st[18]; d[1] = st[19]; d[2] = st[20]; d[3] = st[21]; }
-    double s0[4] = {pa[0], pa[1], pa[2], pa[3]};
-    for (int j = 0; j <= n_full; j++) {
+    for (int base = 0; base <= n_full; base += 32) {
+      const int j = base + lane;
+      double s0[4] = {0., 0., 0., 0.}, r[4] = {0., 0., 0., 0.}, mine[4] = {0., 0., 0., 0.};
+      if (j <= n_full) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        s0[k] = pa[4 * j + k];
-        pa[4 * j + k] = s0[k] + d[k];
+        for (int k = 0; k < 4; k++) s0[k] = pa[4 * j + k];
       }
       if (j < n_full) {
-        double r[4], o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) r[k] = pb[4 * j + k] - pa[4 * (j + 1) + k];   // e1[j] - s0[j+1]: nearly equal, exact
-        hp_apply(M, d, r, o);
-#pragma unroll
-        for (int k = 0; k < 4; k++) d[k] = o[k];
       }
-    }
+      const int steps = min(32, n_full + 1 - base);
+      for (int t = 0; t < steps; t++) {
+        if (lane == t) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      st[14 + k] = s0[k];
-      st[18 + k] = d[k];
-    }
-    if (n_full == n_blocks) {
-      // the chunk ends on a block boundary: the next block starts from (s, 0, s0)
+          for (int k = 0; k < 4; k++) mine[k] = d[k];
+        }
+        double rt[4], o[4];
+        hp_bcast4(r, t, rt);
+        if (base + t < n_full) {
+          hp_apply(M, d, rt, o);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        st[2 + k] = s0[k] + d[k];
-        st[6 + k] = 0.;
-        st[10 + k] = s0[k];
+          for (int k = 0; k < 4; k++) d[k] = o[k];
+        }
+      }
+      __syncwarp();   // every lane has read s0[j + 1] before lane j + 1 overwrites it
+      if (j <= n_full) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) pa[4 * j + k] = s0[k] + mine[k];
+      }
+      if (j == n_full) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          st[14 + k] = s0[k];
+          st[18 + k] = mine[k];
+        }
+        if (n_full == n_blocks) {
+          // the chunk ends on a block boundary: the next block starts from (s, 0, s0)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            st[2 + k] = s0[k] + mine[k];
+            st[6 + k] = 0.;
+            st[10 + k] = s0[k];
+          }
+        }
       }
     }
   }
@@ -417,6 +538,11 @@ __global__ void fb_hp_par_hist_kernel(double* __restrict__ hp, size_t hp_stride,
     const double* src = hp + (size_t)stream * hp_stride + chunk_samples;
     double* dst = hp_state + (size_t)stream * kHpStateDoubles + kHpHdr;
     for (int i = threadIdx.x; i < kFbHist; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {   // x[n-1], x[n-2] left by the output pass
+      double* hdr = hp_state + (size_t)stream * kHpStateDoubles;
+      hdr[0] = hdr[22];
+      hdr[1] = hdr[23];
+    }
   }
 }
 
@@ -609,7 +735,7 @@ __global__ void __launch_bounds__(32 * kRecWarps, 2)
 fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp, size_t hp_stride,
                    unsigned n_sub /* sub-steps in this chunk, a multiple of 6 */, double2* __restrict__ fbout,
                    size_t out_stream_stride /* = 40 * n_sub */, double* __restrict__ hp_state,
-                   int first_chunk) {
+                   int first_chunk, const unsigned* __restrict__ n_frames, unsigned first_frame, int streams_per_pair) {
   extern __shared__ __align__(16) double xs_raw[];   // 2 doubles of padding, [32][kRecStride], then the warps' buffers
   double* xs = xs_raw + 2;                            // (a misaligned 128-bit load may start one double early)
   const int stream = blockIdx.x;
@@ -628,7 +754,11 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
     cst[lane] = (!first_chunk && slot < n_slots) ? carry_state[(warp + kRecWarps * slot) * 3 + f] : make_double2(0., 0.);
   }
   __syncwarp();
-  const int n_tiles = (int)((n_sub + kRecTile - 1) / kRecTile);
+  // tiles that hold frames of this stream's item (nothing downstream reads beyond them; a ragged
+  // batch would otherwise filter zeros for as long as its longest item lasts)
+  const unsigned total = n_frames[stream / streams_per_pair];
+  const unsigned valid = total > first_frame ? min((total - first_frame) * 6u, n_sub) : 0u;
+  const int n_tiles = (int)((valid + kRecTile - 1) / kRecTile);
   const int t_end = (int)(n_sub * 32);
   for (int tile = 0; tile < n_tiles; tile++) {
     const int S0 = tile * kRecTile;
@@ -798,21 +928,21 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
     e = cudaMallocAsync(&sb, n_state * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     const int fc = first_chunk ? 1 : 0;
-    const long long n_threads = (long long)n_streams * n_blocks;
-    const unsigned grid = (unsigned)((n_threads + 63) / 64), sgrid = (unsigned)((n_streams + 31) / 32);
+    const unsigned sgrid = (unsigned)((n_streams + 3) / 4);   // one warp per stream
+    const dim3 grid((unsigned)n_pairs * 2, (unsigned)((n_blocks + kHpTileBlocks - 1) / kHpTileBlocks));
     fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 0, fc);
     if (pcm.channels == 2) {
-      fb_hp_par_block_kernel<2, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
-      fb_hp_par_scan_kernel<0><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
-      fb_hp_par_block_kernel<2, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
-      fb_hp_par_scan_kernel<1><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
-      fb_hp_par_block_kernel<2, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+      fb_hp_par_block_kernel<2, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
+      fb_hp_par_scan_kernel<0><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<2, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+      fb_hp_par_scan_kernel<1><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<2, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
     } else {
-      fb_hp_par_block_kernel<1, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
-      fb_hp_par_scan_kernel<0><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
-      fb_hp_par_block_kernel<1, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
-      fb_hp_par_scan_kernel<1><<<sgrid, 32, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
-      fb_hp_par_block_kernel<1, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_streams, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+      fb_hp_par_block_kernel<1, 0><<<grid, 32, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
+      fb_hp_par_scan_kernel<0><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<1, 1><<<grid, 32, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
+      fb_hp_par_scan_kernel<1><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
+      fb_hp_par_block_kernel<1, 2><<<grid, 32, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
     }
     fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 1, fc);
     cudaFreeAsync(sa, stream);
@@ -835,6 +965,7 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
                            const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
                            double* fbout, double* hp_state, bool first_chunk, bool direct_only,
+                           const unsigned* n_frames, unsigned first_frame, int streams_per_pair,
                            cudaStream_t stream) {
   if (n_streams <= 0 || n_sub == 0) return cudaSuccess;
   // default: all filters through the recursion (fb_bank_rec_kernel); direct_only: all 40 as
@@ -846,7 +977,7 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
     if (e != cudaSuccess) return e;
     fb_bank_rec_kernel<<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
         d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
-        first_chunk ? 1 : 0);
+        first_chunk ? 1 : 0, n_frames, first_frame, streams_per_pair);
     return cudaGetLastError();
   }
   // distribute the 40 bands over the warps, longest filters first, always onto

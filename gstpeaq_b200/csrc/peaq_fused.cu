@@ -66,6 +66,7 @@ peaq_fused_basic_kernel(const DeviceTables* __restrict__ T, PcmView pcm, unsigne
     in.bw = mail->o_bw[th.c];
     in.ehs = mail->o_ehs + th.c;
     in.snr = mail->o_snr;
+    in.dbg = nullptr;
     ScanCounters cnt = *cnt_sh;
     __syncthreads();   // every input is in registers: the FFT buffers are free
     const bool next_ok = f + 1 < end && frame_tma_ok(pcm, pair, f + 1);

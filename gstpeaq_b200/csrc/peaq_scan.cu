@@ -14,11 +14,12 @@ namespace {
 #else
 #define PEAQ_K2_MIN_CTAS 2
 #endif
+template <bool kTap>
 __global__ void __launch_bounds__(kGroup * kMaxChannels, PEAQ_K2_MIN_CTAS)
 scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ records,
                   RecordLayout L, const unsigned* __restrict__ n_frames, unsigned first_frame,
                   unsigned n_chunk_frames, double* __restrict__ state, StateLayout S,
-                  PairResult* __restrict__ results) {
+                  PairResult* __restrict__ results, double* __restrict__ dbg) {
   const int C = L.C, B = L.B;
   const int pair = blockIdx.x;
   const ScanThread th = make_scan_thread(B);
@@ -51,6 +52,7 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
     in.bw = rints + 1 + 2 * th.c;
     in.ehs = rec + L.off_ehs + th.c;
     in.snr = rec + L.off_snr;
+    in.dbg = kTap ? dbg + ((size_t)pair * n_chunk_frames + (f - first_frame)) * scan_tap_doubles(C, B) : nullptr;
 #if defined(PEAQ_DEV_K2_OCC3)
     scan_step(in, MemConst{T, th.bb}, RegState{bs}, RegAcc{}, acc, cnt, sh, th, C, B);
 #else
@@ -70,13 +72,19 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
 
 }  // namespace
 
+int scan_tap_doubles_per_frame(int C, int B) { return scan_tap_doubles(C, B); }
+
 cudaError_t launch_scan_basic(const DeviceTables* d_tables, const double* records, RecordLayout L,
                               const unsigned* n_frames, unsigned first_frame,
                               unsigned n_chunk_frames, double* state, StateLayout S,
-                              PairResult* results, int n_pairs, cudaStream_t stream) {
+                              PairResult* results, int n_pairs, cudaStream_t stream, double* dbg) {
   if (n_pairs <= 0) return cudaSuccess;
-  scan_basic_kernel<<<n_pairs, kGroup * L.C, 0, stream>>>(d_tables, records, L, n_frames, first_frame,
-                                                           n_chunk_frames, state, S, results);
+  if (dbg)
+    scan_basic_kernel<true><<<n_pairs, kGroup * L.C, 0, stream>>>(d_tables, records, L, n_frames, first_frame,
+                                                                  n_chunk_frames, state, S, results, dbg);
+  else
+    scan_basic_kernel<false><<<n_pairs, kGroup * L.C, 0, stream>>>(d_tables, records, L, n_frames, first_frame,
+                                                                   n_chunk_frames, state, S, results, nullptr);
   return cudaGetLastError();
 }
 

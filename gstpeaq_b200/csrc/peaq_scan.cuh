@@ -176,7 +176,12 @@ struct ScanInputs {
   const int* bw;        // {bw_ref, bw_test} of the thread's channel
   const double* ehs;    // EHS value of the thread's channel
   const double* snr;    // {signal, noise} energy of the frame
+  // test tap (keep_records; K2 only) or null: this frame's slot, [2][C][B] smeared excitations
+  // (ref | test) followed by kScanTapValues values per channel, see scan_tap_doubles()
+  double* dbg;
 };
+constexpr int kScanTapValues = 8;   // md1, md2, temporal weight, noise loudness, mean N/M, max N/M, P binaural, Q binaural
+__host__ __device__ inline int scan_tap_doubles(int C, int B) { return 2 * C * B + C * kScanTapValues; }
 
 // status word and counters every thread tracks
 struct ScanCounters {
@@ -301,6 +306,10 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   const double Eft = a_ear * st.get(1) + (1. - a_ear) * E2t;
   st.set(1, Eft);
   const double Et = Eft > E2t ? Eft : E2t;
+  if (in.dbg && active) {
+    in.dbg[(0 * C + c) * B + b] = Er;
+    in.dbg[(1 * C + c) * B + b] = Et;
+  }
 
   // modulation (modpatt.c:234-250): needs nothing but the unsmeared excitations, so it sits in
   // this phase, where its exp/log chain overlaps the detection-probability chain below
@@ -472,6 +481,29 @@ __device__ __forceinline__ void scan_step(const ScanInputs& in, const Konst& kc,
   __syncthreads();   // C
   if (loud_frame == UINT_MAX && latch_sh) loud_frame = frame_counter;
 
+  if (in.dbg && b == 0) {
+    // per-frame terms as the reference's MOV functions see them (before gates and accumulators)
+    double t[kRed2];
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+      t[k] = ((red2[par][c][0][k] + red2[par][c][1][k]) + red2[par][c][2][k]) + red2[par][c][3][k];
+    double mx = red2[par][c][0][5], prod = 1., q = 0.;
+    for (int w = 0; w < kWarpsPerGroup; w++) {
+      if (red2[par][c][w][5] > mx) mx = red2[par][c][w][5];
+      prod *= red2[par][0][w][6];
+      q += red2[par][0][w][7];
+    }
+    double* d = in.dbg + 2 * C * B + c * kScanTapValues;
+    const double nl = t[3] * (24. / B);
+    d[0] = t[0] * (100. / B);
+    d[1] = t[1] * (100. / B);
+    d[2] = t[2];
+    d[3] = nl < 0. ? 0. : nl;
+    d[4] = t[4] / B;
+    d[5] = mx;
+    d[6] = 1. - prod;
+    d[7] = q;
+  }
   // ---- accumulators: thread (c, k) owns slot k of channel c -------------------
   const bool seg_start = frame_counter == cnt.acc_start;   // (frame 0 of a whole item: everything is zero anyway)
   if (acc_thread) {

@@ -126,7 +126,10 @@ int peaq_b200_engine_copy_records(peaq_b200_engine *e, double *dst, size_t max_d
 /* advanced mode, same switch: per 192-sample frame [pair][frame][stream][U|E][40]
  * (unsmeared / smeared filter-bank excitation; stream = 2*channel + (test?1:0)),
  * followed by [pair][frame][channel][8] = mod diff, temp weight, noise loudness,
- * missing components, lin dist, above-threshold flag, 0, 0.  *frames = frames kept. */
+ * missing components, lin dist, above-threshold flag, 0, 0.  *frames = frames kept.
+ * Basic mode: the scan kernel's taps instead, [pair][frame]{[ref|test][channel][109] smeared
+ * excitation, [channel][8] = mod diff 1, mod diff 2, temporal weight, noise loudness, mean N/M,
+ * max N/M, binaural detection probability, binaural detection steps}. */
 int peaq_b200_engine_copy_fb_debug(peaq_b200_engine *e, double *dst, size_t max_doubles,
                                    size_t *n_doubles, uint32_t *frames);
 /* constant tables of the engine for a mode / playback level (host code, no

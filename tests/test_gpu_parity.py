@@ -111,6 +111,42 @@ def test_per_frame_records_match_oracle(engine, name):
     np.testing.assert_allclose(np.cumsum(rec["snr"][0][:, 1]), tr["noise_energy"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["synth0_stereo", "synth5_mono", "noise_silence_stereo", "noise_loud_mono"])
+def test_per_frame_scan_terms_match_oracle(engine, name):
+    """K2's per-frame taps against the oracle's trace: time-smeared excitation patterns, and the
+    band-summed terms the MOV functions hand to the accumulators (modulation differences and
+    temporal weight from frame 24 on, noise loudness once the loudness latch + 3 frames allows,
+    N/M mean and maximum, binaural detection probability and steps)."""
+    ref, test, ch = golden_cases()[name]
+    nf = G.frames_for_samples(ref.size // ch)
+    o = H.OraclePeaq(False, 92.0, ch, fft_trace=nf)
+    o.run(ref, test)
+    tr = o.fft_trace
+    engine.keep_records(True)
+    try:
+        out = engine.run_host(ref, test, ch)
+        exc, terms = engine.scan_debug(1, ch)
+    finally:
+        engine.keep_records(False)
+    B = 109
+    exc, terms = exc[0, :nf], terms[0, :nf]
+    np.testing.assert_allclose(exc, tr["excitation"][:, :, :ch, :B], rtol=1e-10)
+    f = np.arange(nf)
+    md = f >= 24
+    np.testing.assert_allclose(terms[md, :, 0], tr["mod_diff1"][md][:, :ch], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(terms[md, :, 1], tr["mod_diff2"][md][:, :ch], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(terms[md, :, 2], tr["temp_wt"][md][:, :ch], rtol=1e-9)
+    loud = int(out["loudness_reached_frame"][0])
+    nl = md & (f.astype(np.int64) - 3 >= loud)
+    if nl.any():
+        np.testing.assert_allclose(terms[nl, :, 3], tr["noise_loud"][nl][:, :ch], rtol=1e-8, atol=1e-11)
+    # the noise-to-mask ratios inherit the cancellation of noise_in_bands (see the record test)
+    np.testing.assert_allclose(terms[:, :, 4], tr["nmr"][:, :ch], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(terms[:, :, 5], tr["nmr_max"][:, :ch], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(terms[:, 0, 6], tr["det_prob"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(terms[:, 0, 7], tr["adb_steps"], rtol=1e-8, atol=1e-9)
+
+
 def test_batch_of_ragged_synthetic_pairs_matches_oracle(engine):
     """one call, pairs of different lengths (incl. empty and sub-frame items)"""
     ch = 2
