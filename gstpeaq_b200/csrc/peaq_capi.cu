@@ -41,6 +41,14 @@ static_assert(sizeof(PairResult) == sizeof(peaq_b200_result), "result layout mis
 // Fresh recurrent state: everything zero (g_new0 in the reference's
 // constructors), accumulators in STATUS_INIT, the windowed-average history
 // primed with NaN (movaccum.c:293), loudness not yet reached (gstpeaq.c:359).
+// Small tables (plans, segment words) are FETCHED from pinned host memory by a kernel on the
+// compute stream instead of being copied: a cudaMemcpyAsync would share the copy engine with the
+// staging copies of the next sub-batch and wait behind gigabytes of PCM.
+__global__ void fetch_words_kernel(unsigned* __restrict__ dst, const unsigned* __restrict__ src, size_t n_words) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
 __global__ void init_state_kernel(double* state, StateLayout S, int n_pairs) {
   const size_t total = (size_t)n_pairs * S.stride;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -165,8 +173,65 @@ struct Engine {
   size_t stage_cap[2] = {0, 0};   // floats, per buffer of the slot
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_freed[2] = {nullptr, nullptr};
-  std::vector<std::vector<unsigned long long>> plan_hold_ns;   // keep async H2D sources alive
-  std::vector<std::vector<unsigned>> plan_hold_nf;
+  // Small host <-> device transfers of a batch (plans, segment tables, redo flags) go through
+  // PINNED memory: from pageable memory cudaMemcpyAsync first drains the stream (H2D) or waits for
+  // the copy (D2H), which would serialise the staging copies of the next sub-batch behind the
+  // kernels of this one.  The arena is recycled when the batch has been synchronised.
+  struct PinnedArena {
+    std::vector<std::pair<char*, size_t>> blocks;
+    size_t cur = 0, used = 0;
+    void* take(size_t bytes) {
+      bytes = (bytes + 63) & ~(size_t)63;
+      while (cur < blocks.size() && used + bytes > blocks[cur].second) {
+        cur++;
+        used = 0;
+      }
+      if (cur == blocks.size()) {
+        const size_t cap = std::max<size_t>(bytes, (size_t)1 << 20);
+        char* p = nullptr;
+        if (cudaHostAlloc((void**)&p, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {   // kernels read / write it
+          cudaGetLastError();
+          return nullptr;
+        }
+        blocks.emplace_back(p, cap);
+        used = 0;
+      }
+      void* r = blocks[cur].first + used;
+      used += bytes;
+      return r;
+    }
+    void reset() { cur = 0; used = 0; }
+    void destroy() {
+      for (auto& b : blocks) cudaFreeHost(b.first);
+      blocks.clear();
+      reset();
+    }
+  } arena;
+  struct DeferredCopy {   // arena -> caller memory, once the batch has been synchronised
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<DeferredCopy> deferred;
+  // device <- pinned host memory through fetch_words_kernel, on the compute stream
+  template <typename T>
+  int fetch(T* d_dst, const T* pinned_src, size_t n) {
+    static_assert(sizeof(T) % 4 == 0, "whole words");
+    const size_t words = n * (sizeof(T) / 4);
+    if (!words) return 0;
+    const unsigned blocks = (unsigned)std::min<size_t>((words + 255) / 256, 64);
+    fetch_words_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<unsigned*>(d_dst),
+                                                   reinterpret_cast<const unsigned*>(pinned_src), words);
+    PEAQ_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // pinned copy of a small host array (alive until finish_batch)
+  template <typename T>
+  const T* pinned_copy(const T* src, size_t n) {
+    T* p = static_cast<T*>(arena.take(std::max<size_t>(n, 1) * sizeof(T)));
+    if (p && n) std::memcpy(p, src, n * sizeof(T));
+    return p;
+  }
   std::vector<EventPair> events;
   size_t events_used = 0;
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // see peaq_b200_engine_last_ms; [7]: flags + DC-reject scan
@@ -187,8 +252,6 @@ struct Engine {
   size_t seg_base_cap = 0;
   unsigned* d_seg_words = nullptr;   // [5][n_vp]: segment index, frame0 / acc_start of both clocks; then [2][n_items]
   size_t seg_words_cap = 0;
-  unsigned char* d_seg_redo = nullptr;
-  size_t seg_redo_cap = 0;
   PairResult* d_item_results = nullptr;
   size_t item_results_cap = 0;
 
@@ -196,6 +259,16 @@ struct Engine {
     PEAQ_CUDA(cudaSetDevice(device));
     PEAQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     PEAQ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    {
+      // scratch of the stream-ordered allocator (the DC-reject block scan's block states) stays
+      // with the process between batches instead of going back to the driver at every sync
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    }
     {
       int prio_lo = 0, prio_hi = 0;
       PEAQ_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -261,9 +334,9 @@ struct Engine {
     cudaFree(d_records);
     cudaFree(d_state);
     cudaFree(d_results);
+    arena.destroy();
     cudaFree(d_seg_base);
     cudaFree(d_seg_words);
-    cudaFree(d_seg_redo);
     cudaFree(d_item_results);
     cudaFree(d_nsamples);
     cudaFree(d_nframes);
@@ -368,20 +441,16 @@ struct Engine {
   };
 
   int upload_plan(const ClockPlan& plan, int n_pairs, int slot) {
-    // the host copies stay alive in plan_hold_* until the batch has been synchronised
-    plan_hold_ns.emplace_back(plan.ns_ref, plan.ns_ref + n_pairs);
-    const unsigned long long* a = plan_hold_ns.back().data();
-    plan_hold_ns.emplace_back(plan.ns_test, plan.ns_test + n_pairs);
-    const unsigned long long* b = plan_hold_ns.back().data();
-    plan_hold_nf.emplace_back(plan.nf, plan.nf + n_pairs);
-    const unsigned* f = plan_hold_nf.back().data();
-    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot) * pairs_cap, a, n_pairs * sizeof(unsigned long long),
-                              cudaMemcpyHostToDevice, stream));
-    PEAQ_CUDA(cudaMemcpyAsync(d_nsamples + (size_t)(2 * slot + 1) * pairs_cap, b,
-                              n_pairs * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    PEAQ_CUDA(cudaMemcpyAsync(d_nframes + (size_t)slot * pairs_cap, f, n_pairs * sizeof(unsigned),
-                              cudaMemcpyHostToDevice, stream));
-    return 0;
+    // pinned host copies, alive until the batch has been synchronised
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "plan words");
+    const unsigned long long* a = pinned_copy(reinterpret_cast<const unsigned long long*>(plan.ns_ref), (size_t)n_pairs);
+    const unsigned long long* b = pinned_copy(reinterpret_cast<const unsigned long long*>(plan.ns_test), (size_t)n_pairs);
+    const unsigned* f = pinned_copy(plan.nf, (size_t)n_pairs);
+    if (!a || !b || !f) return fail(PEAQ_B200_ERR_NOMEM, "out of pinned host memory");
+    int rc;
+    if ((rc = fetch(d_nsamples + (size_t)(2 * slot) * pairs_cap, a, (size_t)n_pairs))) return rc;
+    if ((rc = fetch(d_nsamples + (size_t)(2 * slot + 1) * pairs_cap, b, (size_t)n_pairs))) return rc;
+    return fetch(d_nframes + (size_t)slot * pairs_cap, f, (size_t)n_pairs);
   }
 
   PcmView make_view(const float* d_ref, const float* d_test, size_t pair_stride, int C, int slot) const {
@@ -498,18 +567,18 @@ struct Engine {
     int rc;
     if ((rc = ensure(&d_seg_base, &seg_base_cap, (size_t)n_vp))) return rc;
     if ((rc = ensure(&d_seg_words, &seg_words_cap, (size_t)5 * n_vp + (size_t)2 * sp.n_items))) return rc;
-    plan_hold_ns.emplace_back(sp.base);
-    PEAQ_CUDA(cudaMemcpyAsync(d_seg_base, plan_hold_ns.back().data(), (size_t)n_vp * sizeof(unsigned long long),
-                              cudaMemcpyHostToDevice, stream));
+    const unsigned long long* base = pinned_copy(sp.base.data(), (size_t)n_vp);
+    if (!base) return fail(PEAQ_B200_ERR_NOMEM, "out of pinned host memory");
+    if ((rc = fetch(d_seg_base, base, (size_t)n_vp))) return rc;
     std::vector<unsigned> words;
     words.reserve((size_t)5 * n_vp + (size_t)2 * sp.n_items);
     for (const auto* v : {&sp.seg_index, &sp.frame0_fft, &sp.acc_start_fft, &sp.frame0_fb, &sp.acc_start_fb})
       words.insert(words.end(), v->begin(), v->end());
     words.insert(words.end(), sp.first_vp.begin(), sp.first_vp.end());
     words.insert(words.end(), sp.n_seg.begin(), sp.n_seg.end());
-    plan_hold_nf.emplace_back(std::move(words));
-    PEAQ_CUDA(cudaMemcpyAsync(d_seg_words, plan_hold_nf.back().data(), plan_hold_nf.back().size() * sizeof(unsigned),
-                              cudaMemcpyHostToDevice, stream));
+    const unsigned* pw = pinned_copy(words.data(), words.size());
+    if (!pw) return fail(PEAQ_B200_ERR_NOMEM, "out of pinned host memory");
+    if ((rc = fetch(d_seg_words, pw, words.size()))) return rc;
     const unsigned* w = d_seg_words;
     t->seg_index = reinterpret_cast<const int*>(w);
     t->frame0_fft = w + (size_t)n_vp;
@@ -753,14 +822,16 @@ struct Engine {
       // sums of the segments -> segment 0 of every item, the scan kernels' epilogues once more
       // (zero frames) on the combined state, then one result row per item
       n_out = seg->n_items;
-      if ((rc = ensure(&d_seg_redo, &seg_redo_cap, (size_t)n_out))) return rc;
       if ((rc = ensure(&d_item_results, &item_results_cap, (size_t)n_out))) return rc;
+      // the redo flags are written straight into pinned host memory (no copy engine, see fetch())
+      unsigned char* redo_pin = static_cast<unsigned char*>(arena.take((size_t)n_out));
+      if (!redo_pin) return fail(PEAQ_B200_ERR_NOMEM, "out of pinned host memory");
       if (!advanced) {
-        PEAQ_CUDA(launch_seg_combine(d_state, &S, nullptr, n_out, seg_table, d_seg_redo, stream));
+        PEAQ_CUDA(launch_seg_combine(d_state, &S, nullptr, n_out, seg_table, redo_pin, stream));
         PEAQ_CUDA(launch_scan_basic(d_tables, d_records, L, pcm.n_frames, 0, 0, d_state, S, d_res, n_pairs, stream));
         launches += 2;
       } else {
-        PEAQ_CUDA(launch_seg_combine(d_state, nullptr, &A, n_out, seg_table, d_seg_redo, stream));
+        PEAQ_CUDA(launch_seg_combine(d_state, nullptr, &A, n_out, seg_table, redo_pin, stream));
         PEAQ_CUDA(launch_fb_scan(d_tables, d_fbenergy, 0, d_fbflags, pcm.n_frames, 0, 0, d_state, A, nullptr, n_pairs,
                                  stream));
         PEAQ_CUDA(launch_adv_fft_scan(d_tables, d_records, L, pcm.n_frames, 0, 0, d_state, A, d_res, n_pairs, stream));
@@ -770,8 +841,7 @@ struct Engine {
       PEAQ_CUDA(launch_seg_gather_results(d_res, seg_table.first_vp, n_out, d_items, stream));
       launches++;
       d_res = d_items;
-      if (h_redo)
-        PEAQ_CUDA(cudaMemcpyAsync(h_redo, d_seg_redo, (size_t)n_out, cudaMemcpyDeviceToHost, stream));
+      if (h_redo) deferred.push_back({h_redo, redo_pin, (size_t)n_out});
     }
     if (!blocking) return 0;
     if (h_out) {
@@ -852,8 +922,9 @@ struct Engine {
 
   int finish_batch() {
     PEAQ_CUDA(cudaStreamSynchronize(stream));
-    plan_hold_ns.clear();
-    plan_hold_nf.clear();
+    for (const auto& d : deferred) std::memcpy(d.dst, d.src, d.bytes);
+    deferred.clear();
+    arena.reset();
     return timers_collect();
   }
 };
@@ -884,8 +955,8 @@ struct BatchCleanup {
     cudaStreamSynchronize(e->copy_stream);
     if (e->scan_stream) cudaStreamSynchronize(e->scan_stream);
     e->events_used = 0;
-    e->plan_hold_ns.clear();
-    e->plan_hold_nf.clear();
+    e->deferred.clear();
+    e->arena.reset();
     cudaGetLastError();
   }
 };
@@ -944,21 +1015,35 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
     // ~100 ns of kernels), so the job takes all copies plus the kernels of the LAST sub-batch:
     // small, equal sub-batches (one wave of the scan kernel's CTAs, two per SM).  Advanced mode
     // is bound by the kernels, so it takes the FIRST copy plus all kernels: a small first
-    // sub-batch, then large ones.
+    // sub-batch, then growing ones.
     std::vector<int> sizes;
     {
+      // the counts below were tuned on 10 s stereo pairs (3.84 MB per signal); longer items weigh
+      // as many of those as they are long, so that sub-batches keep their size in bytes
+      const double weight = std::max(1.0, (double)stride / 960000.0);
+      auto pairs_of = [&](int standard_pairs) { return std::max(1, (int)(standard_pairs / weight)); };
       int left = n_pairs;
-      if (e->advanced && left > 256) {
-        // measured best among 128 / 256-doubling / 640 first (1068 / 1092 / 1108 ms per 4096 pairs)
-        sizes.push_back(std::min(per_max, 128));
-        left -= sizes.back();
-      }
-      const int per = std::min(per_max, e->advanced ? 1024 : (e->fused_mode == 1 ? 3 : 2) * e->sm_count);
-      while (left > 0) {
-        // basic mode: the very last sub-batches small, the job ends with their kernels
-        const int n = (!e->advanced && left <= per) ? std::min(left, 128) : std::min(per, left);
-        sizes.push_back(n);
-        left -= n;
+      if (e->advanced) {
+        // kernel-bound (0.19 ms of kernels against 0.14 ms of copies per standard pair): the job
+        // takes the FIRST copy plus all kernels as long as no later copy outlasts the kernels of
+        // the sub-batch before it -- sub-batches grow by 1.4 x from 128 standard pairs (one
+        // 128 + 4 x 1024 schedule left 140 ms of the second copy exposed: 943 ms per 4096 pairs)
+        double next = 128;
+        while (left > 0) {
+          int n = std::min({left, per_max, pairs_of((int)next)});
+          if (left - n < pairs_of(64)) n = std::min(left, per_max);   // no crumbs at the end
+          sizes.push_back(n);
+          left -= n;
+          next = std::min(next * 1.4, 1200.0);
+        }
+      } else {
+        const int per = std::min(per_max, pairs_of((e->fused_mode == 1 ? 3 : 2) * e->sm_count));
+        while (left > 0) {
+          // copy-bound: the job ends with the kernels of the last sub-batches, which are small
+          const int n = left <= per ? std::min(left, pairs_of(128)) : std::min(per, left);
+          sizes.push_back(n);
+          left -= n;
+        }
       }
     }
     // size everything once, for the largest sub-batch: growing later would free memory under

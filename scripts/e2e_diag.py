@@ -7,7 +7,7 @@ import gstpeaq_b200 as G
 def main():
     n_pairs = int(os.environ.get("PEAQ_PROFILE_PAIRS", "4096"))
     advanced = int(os.environ.get("PEAQ_PROFILE_ADVANCED", "1"))
-    ns, ch = 480000, 2
+    ns, ch = 48000 * int(os.environ.get("PEAQ_PROFILE_SECONDS", "10")), 2
     L = G.load_library()
     eng = G.Engine(0, advanced=bool(advanced))
     nbytes = n_pairs * ns * ch * 4

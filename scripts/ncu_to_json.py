@@ -67,8 +67,8 @@ def main():
     for spec in sys.argv[4:]:
         name, kernel = spec.split("=")
         p = os.path.join(d, name + ".raw.csv")
-        if not os.path.exists(p):
-            print("missing", p)
+        if not os.path.exists(p) or sum(1 for _ in open(p)) < 3:
+            print("missing", p, file=sys.stderr)
             continue
         doc["kernels"][kernel] = facts(read_raw(p), frames, "profiles/%s_%s_ncu.txt" % (tag, name))
     json.dump(doc, open(os.path.join(ROOT, "profiles", "ncu_kernels.json"), "w"), indent=1)

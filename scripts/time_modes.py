@@ -16,11 +16,14 @@ def main():
     for adv in ([0, 1] if which == "both" else [1 if which == "advanced" else 0]):
         eng = G.Engine(0, advanced=bool(adv))
         best = None
-        for i in range(4):
+        every = []
+        for i in range(5):
             out = eng.run_device(dref.ptr, dtest.ptr, n_pairs, ns * ch, ch, ns)
             t = [eng.last_ms(k) for k in range(7)]
+            every.append(round(t[0], 1))
             if i and (best is None or t[0] < best[0]):
                 best = t
+        print("  totals of the passes (ms):", every)
         fr = int(out["frames_fft"].sum())
         print("%s adv %d pairs %d x %d s: total %.1f ms (frames %.1f scan %.1f fb-all %.1f bank %.1f spread+scan %.1f) -> %.3f M frames/s  odg[0..2] %s" % (
             os.path.basename(G.library_path()), adv, n_pairs, seconds, best[0], best[1], best[2], best[4], best[5], best[6],
