@@ -545,7 +545,7 @@ def our_arm(args):
     c = make_ctx(args)
     cores = os.cpu_count() or 1
     single = c.world == 1
-    pairs_gpu = pairs_per_gpu(c.world)
+    pairs_gpu = args.pairs_per_gpu or pairs_per_gpu(c.world)
 
     def cpu_n(mode, cap):
         # N = 1: the bounded CPU baseline sample; N > 1: a small parity sample only
@@ -571,7 +571,7 @@ def our_arm(args):
             n_cpu = 0
             if not args.no_cpu_baseline and sec <= 600:
                 n_cpu = min(LONG_PAIRS_PER_GPU, cores) if single else min(LONG_PAIRS_PER_GPU, cores, 4)
-            r, _ = measure(c, mode, LONG_PAIRS_PER_GPU, sec, 2, 1, n_cpu, 1,
+            r, _ = measure(c, mode, LONG_PAIRS_PER_GPU, sec, 3, 2, n_cpu, 1,
                            "long items: first pairs of the long-item workload itself")
             long_res[mode] = r
         extra["long_items"] = long_res
@@ -622,6 +622,8 @@ def main():
                     help="item length of the long_items section (BASELINE configs[4] is 3600; the default keeps "
                          "the whole run and its CPU parity sample within minutes)")
     ap.add_argument("--long-seconds-advanced", type=int, default=0)
+    ap.add_argument("--pairs-per-gpu", type=int, default=0,
+                    help="headline batch per GPU (default: 4096 = BASELINE configs[1]; 8192 at 8 GPUs = configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
