@@ -49,8 +49,9 @@ UNIT = "frames/s"
 ODG_LIMIT = 1e-4                                  # SURVEY 8d parity gate
 # CPU sample sizes (pairs per host core): about 3 s (basic) / 3 s (advanced) of work per core
 CPU_PAIRS_PER_CORE = {"basic": 12, "advanced": 4}
-KERNEL_SOURCES = ["peaq_frames.cu", "peaq_fft.cuh", "peaq_scan.cu", "peaq_fused.cu", "peaq_fb.cu",
-                  "peaq_scan_adv.cu", "peaq_math.cuh", "peaq_engine.h"]
+KERNEL_SOURCES = ["peaq_frames.cu", "peaq_frames.cuh", "peaq_fft.cuh", "peaq_scan.cu", "peaq_scan.cuh",
+                  "peaq_fused.cu", "peaq_fb.cu", "peaq_scan_adv.cu", "peaq_segments.cu", "peaq_math.cuh",
+                  "peaq_engine.h"]
 
 
 def frames_for(n_samples):

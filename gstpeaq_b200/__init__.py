@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "peaq_b200_session_get_result", "peaq_b200_fp64_peak_tflops",
     "peaq_b200_session_snapshot", "peaq_b200_session_restore",
     "peaq_b200_multi_create", "peaq_b200_multi_destroy", "peaq_b200_multi_device_count",
-    "peaq_b200_multi_run_batch",
+    "peaq_b200_multi_run_batch", "peaq_b200_segment_plan",
 ]
 
 MOV_NAMES_BASIC = ["BandwidthRefB", "BandwidthTestB", "Total NMRB", "WinModDiff1B", "ADBB", "EHSB",
@@ -166,6 +166,17 @@ def frames_for_samples(n):
     full = (n - FFT_FRAME) // FFT_STEP + 1 if n >= FFT_FRAME else 0
     left = n - full * FFT_STEP
     return full + (1 if left > 0 else 0)
+
+
+def segment_plan(n_samples):
+    """(segments, segment length, warm-up) in samples for a batch item of n_samples per channel
+    (host code; see peaq_b200_segment_plan)."""
+    L = load_library()
+    L.peaq_b200_segment_plan.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.peaq_b200_segment_plan.restype = C.c_int
+    seg, warm = C.c_uint64(), C.c_uint64()
+    k = L.peaq_b200_segment_plan(int(n_samples), C.byref(seg), C.byref(warm))
+    return int(k), int(seg.value), int(warm.value)
 
 
 def synth_pairs_host(first_pair, n_pairs, n_samples, channels=2):

@@ -1680,6 +1680,14 @@ int peaq_b200_engine_copy_fb_debug(peaq_b200_engine* h, double* dst, size_t max_
   return 0;
 }
 
+int peaq_b200_segment_plan(uint64_t n_samples, uint64_t* segment_samples, uint64_t* warmup_samples) {
+  uint64_t len = 0;
+  const unsigned k = Engine::segments_for_samples(n_samples, &len);
+  if (segment_samples) *segment_samples = len;
+  if (warmup_samples) *warmup_samples = kSegWarmSamples;
+  return (int)k;
+}
+
 int peaq_b200_table(int advanced, double playback_level, int model, int which, double* out) {
   if (!out) return fail(PEAQ_B200_ERR_INVALID, "null argument");
   DeviceTables* tp = new (std::nothrow) DeviceTables;

@@ -138,6 +138,12 @@ int peaq_b200_engine_copy_fb_debug(peaq_b200_engine *e, double *dst, size_t max_
  * tables of band `which` -- N, D, recursion coefficients [32][6] and rotations [3][6]
  * (complex), then the taps re[0..N/2], im[0..N/2]; `out` must hold 1880 doubles */
 int peaq_b200_table(int advanced, double playback_level, int model, int which, double *out);
+/* How a batch item of n_samples per channel is run (host code, no GPU needed): the number of
+ * segments it is cut into (1: not cut), their length and the warm-up every segment after the
+ * first starts with, in samples.  Long items run as segments so that a handful of hour-long
+ * pairs fill the GPU (gstpeaq_b200/csrc/peaq_segments.cu); the cut depends on n_samples alone.
+ * Environment PEAQ_B200_SEGMENTS=0 switches segments off; sessions never use them. */
+int peaq_b200_segment_plan(uint64_t n_samples, uint64_t *segment_samples, uint64_t *warmup_samples);
 
 /* ------------------------------------------------------------------------
  * Session: one element instance (struct _GstPeaq, gstpeaq.c:110-139).

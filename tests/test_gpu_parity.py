@@ -859,6 +859,13 @@ def test_segmented_long_items_match_oracle_and_the_whole_run(monkeypatch, advanc
     seg = _run_one(monkeypatch, advanced, ref, test, ch, ns, PEAQ_B200_SEGMENTS="1")
     whole = _run_one(monkeypatch, advanced, ref, test, ch, ns, PEAQ_B200_SEGMENTS="0")
     assert seg[2].tobytes() == whole[2].tobytes()          # the short item is not touched
+    # where an item is cut depends on its length alone: same bits in any batch, at any position
+    rev = _run_one(monkeypatch, advanced, ref[::-1].copy(), test[::-1].copy(), ch, ns[::-1].copy(),
+                   PEAQ_B200_SEGMENTS="1")
+    assert rev[::-1].tobytes() == seg.tobytes()
+    alone = _run_one(monkeypatch, advanced, ref[:1, :lengths[0] * ch].copy(), test[:1, :lengths[0] * ch].copy(), ch,
+                     None, PEAQ_B200_SEGMENTS="1")
+    assert alone[0].tobytes() == seg[0].tobytes()
     n = 5 if advanced else 11
     for p in range(3):
         for k in ("frames_fft", "frames_fb", "loudness_reached_frame", "n_movs"):

@@ -188,3 +188,22 @@ def test_time_parallel_dc_reject_scan_algorithm_in_numpy():
     assert np.abs(fine - ref).max() < 5e-11 * rms
     assert np.abs(fine - ref).max() < 0.2 * np.abs(coarse - ref).max()   # the refinement is what gets it there
     assert np.abs(M).max() > 50      # the ill-conditioning that makes it necessary
+
+
+def test_segment_plan_of_long_items():
+    """peaq_segments.cu: items are cut by their length alone, into equally long segments whose
+    boundaries lie on whole frames of both clocks (1024 / 192 samples) and on the DC-reject scan's
+    512-sample blocks; the warm-up is 4.096 s; at most 512 segments per item."""
+    for n in (0, 1, 480000, 48000 * 49, 48000 * 50, 48000 * 100, 48000 * 600, 48000 * 3600, 48000 * 3600 * 8 + 12345):
+        k, seg, warm = G.segment_plan(n)
+        assert warm == 196608 and warm % 1024 == 0 and warm % 192 == 0 and warm % 512 == 0
+        assert 1 <= k <= 512
+        if n <= 48000 * 49:
+            assert k == 1                      # BASELINE configs[1..3] items are never cut
+            continue
+        assert seg % 3072 == 0 and seg >= 4 * warm
+        assert (k - 1) * seg < n <= k * seg    # equal lengths, a non-empty last segment
+        if k < 512:
+            assert abs(seg / 48000. - 32.768) < 11.    # about 33 s each
+    assert G.segment_plan(48000 * 600) == (18, 1600512, 196608)
+    assert G.segment_plan(48000 * 3600)[0] == 110
