@@ -423,9 +423,14 @@ def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, wh
     frames_step = int(full["frames_fft"].sum())
     assert frames_step == n_global * fpp, (frames_step, n_global * fpp)
     value = frames_step / (step_ms / 1e3)
+    cfg = workload_config(c.world, mode, pairs_gpu, seconds)
+    k_seg, seg_len, seg_warm = G.segment_plan(n_samples)
+    if k_seg > 1:
+        cfg["segments"] = ("every item runs as %d segments of %.1f s, each after the first with a %.3f s warm-up "
+                           "(gstpeaq_b200/csrc/peaq_segments.cu)" % (k_seg, seg_len / 48000., seg_warm / 48000.))
     res = {"value": value, "unit": UNIT, "ms_per_step": step_ms, "wall_ms_per_step": wall_ms,
            "gather_ms_per_step": gather_ms, "steps": steps, "warmup": warmup,
-           "config": workload_config(c.world, mode, pairs_gpu, seconds), "clocks": clocks,
+           "config": cfg, "clocks": clocks,
            "gpu_launches": int(launches), "nan_odg_pairs": int(np.isnan(full["odg"]).sum()),
            "odg_min": float(np.nanmin(full["odg"])), "odg_max": float(np.nanmax(full["odg"]))}
 

@@ -137,7 +137,7 @@ __device__ __forceinline__ double group_band(const DeviceTables* __restrict__ T,
 // noise spectrum bin (movs.c:993-998)
 __device__ __forceinline__ double noise_bin(const double* spec_ref, const double* spec_test, int k) {
   const double r = spec_ref[k], t = spec_test[k];
-  return r - 2 * sqrt(r * t) + t;
+  return r - 2 * peaq_sqrt(r * t) + t;
 }
 
 // noise_in_bands[i] (movs.c:999-1000): the grouping of fftearmodel.c:603-620 applied to the noise
