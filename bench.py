@@ -458,16 +458,20 @@ def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, wh
         eng._run(pr.value, pt.value, e2e_pairs, stride, CHANNELS, None, n_samples, on_device=False)  # warm-up
         barrier(c)
         t0 = time.perf_counter()
+        each = []
         for _ in range(e2e_steps):
+            t1 = time.perf_counter()
             o2 = eng._run(pr.value, pt.value, e2e_pairs, stride, CHANNELS, None, n_samples, on_device=False)
             if c.dist is not None:
                 parallel.gather_results(o2, e2e_pairs * c.world, dev)
+            each.append(round((time.perf_counter() - t1) * 1e3, 1))
         barrier(c)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         e2e_ms = allmax(c, [e2e_ms])[0]
         res["e2e"] = {"value": e2e_pairs * c.world * fpp / (e2e_ms / 1e3), "unit": UNIT,
                       "h2d_bytes_per_step": 2 * hb * c.world, "d2h_bytes_per_step": e2e_pairs * c.world * 128,
-                      "ms_per_step": e2e_ms, "pairs_per_gpu": e2e_pairs, "steps": e2e_steps,
+                      "ms_per_step": e2e_ms, "ms_of_each_step_rank0": each, "pairs_per_gpu": e2e_pairs,
+                      "steps": e2e_steps,
                       "host_memory": "pinned",
                       "bit_equal_to_resident_run": bool(np.array_equal(o2["odg"], out["odg"][:e2e_pairs], equal_nan=True))}
         L.peaq_b200_host_free_pinned(pr.value)

@@ -23,7 +23,7 @@ import os
 import numpy as np
 
 __all__ = ["Peaq", "Engine", "MultiEngine", "PeaqError", "Result", "library_path", "load_library",
-           "device_count", "synth_pairs_host", "frames_for_samples", "fb_filter_tables", "ABI_SYMBOLS"]
+           "device_count", "synth_pairs_host", "frames_for_samples", "segment_plan", "fb_filter_tables", "ABI_SYMBOLS"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 

@@ -30,7 +30,8 @@ PEAQ_B200_FUSED=1 cap peaq_fused_basic_kernel 0 1 fused_basic
 cap fb_bank_rec_kernel 1 1 fb_bank_rec
 cap fb_spread_kernel 1 1 fb_spread
 cap fb_scan_kernel 1 1 fb_scan
-cap "fb_hp_par_block_kernel<2,.2>" 1 1 fb_hp_par_out
-cap "fb_hp_par_block_kernel<2,.0>" 1 1 fb_hp_par_zero
+# the block passes of the DC-reject scan: zero-state, from-s0 and output pass per run (skip the first run)
+cap fb_hp_par_block_kernel 1 3 fb_hp_par_zero
+cap fb_hp_par_block_kernel 1 5 fb_hp_par_out
 cap fft_frames_kernel 1 1 fft_frames_adv
 ls -la $OUT
