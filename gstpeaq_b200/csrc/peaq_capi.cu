@@ -1028,13 +1028,19 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
         // takes the FIRST copy plus all kernels as long as no later copy outlasts the kernels of
         // the sub-batch before it -- sub-batches grow by 1.4 x from 128 standard pairs (one
         // 128 + 4 x 1024 schedule left 140 ms of the second copy exposed: 943 ms per 4096 pairs)
-        double next = 128;
+        // ... and no sub-batch so small that it cannot fill the GPU: at least 128 pairs or
+        // segments (a 10-minute item is 18 segments: 8 items)
+        uint64_t seg_len = 0;
+        const int vp_per_pair = e->segment_mode && !e->keep_records ? (int)Engine::segments_for_samples(max_n, &seg_len) : 1;
+        const int floor_pairs = std::min(per_max, std::max(pairs_of(128), (128 + vp_per_pair - 1) / vp_per_pair));
+        double next = floor_pairs;
+        const int cap = std::max(floor_pairs, pairs_of(1200));
         while (left > 0) {
-          int n = std::min({left, per_max, pairs_of((int)next)});
-          if (left - n < pairs_of(64)) n = std::min(left, per_max);   // no crumbs at the end
+          int n = std::min({left, per_max, std::max(floor_pairs, (int)next)});
+          if (left - n < std::max(1, floor_pairs / 2)) n = std::min(left, per_max);   // no crumbs at the end
           sizes.push_back(n);
           left -= n;
-          next = std::min(next * 1.4, 1200.0);
+          next = std::min(next * 1.4, (double)cap);
         }
       } else {
         const int per = std::min(per_max, pairs_of((e->fused_mode == 1 ? 3 : 2) * e->sm_count));
@@ -1045,6 +1051,11 @@ static int run_batch(Engine* e, const peaq_b200_batch* b, peaq_b200_result* out)
           left -= n;
         }
       }
+    }
+    if (std::getenv("PEAQ_B200_DEBUG")) {
+      std::fprintf(stderr, "peaq_b200: %d sub-batches:", (int)sizes.size());
+      for (int n : sizes) std::fprintf(stderr, " %d", n);
+      std::fprintf(stderr, " pairs\n");
     }
     // size everything once, for the largest sub-batch: growing later would free memory under
     // queued kernels (cudaFree synchronises the device and stalls the copy / compute overlap)
