@@ -906,3 +906,22 @@ def test_segments_fall_back_to_the_whole_item_when_their_assumptions_fail(monkey
     finally:
         e.close()
     assert dev.tobytes() == seg.tobytes()
+
+
+def test_ten_minute_advanced_item_bounds_the_filter_bank_drift(monkeypatch):
+    """The filter bank runs as marginally stable recursions (sliding windowed DFTs, |r| = 1) whose
+    rounding error random-walks with the item length.  A 10-minute mono item (150 000 filter-bank
+    frames, 900 000 sub-steps) against the oracle's direct FIR filters, once as ONE sequential
+    chain (segments off: the recursion never restarts) and once as 18 segments: MOVs to 1e-9
+    (observed ~1e-12; the walk grows with the square root of the length, so an hour-long
+    sequential session stays below 3e-9), ODG to 1e-9."""
+    ch = 1
+    n = 48000 * 600
+    r, t = G.synth_pairs_host(950, 1, n, ch)
+    want = H.oracle_run_pair(r[0], t[0], ch, advanced=True)
+    for seg in ("0", "1"):
+        out = _run_one(monkeypatch, True, r, t, ch, None, PEAQ_B200_SEGMENTS=seg)
+        assert int(out["frames_fb"][0]) == want["frames_fb"] == 150000
+        assert int(out["frames_fft"][0]) == want["frames_fft"]
+        np.testing.assert_allclose(out["movs"][0][:5], want["movs"], rtol=1e-9, atol=1e-12, err_msg="segments " + seg)
+        assert abs(out["odg"][0] - want["odg"]) < 1e-9 and abs(out["di"][0] - want["di"]) < 1e-9
