@@ -932,13 +932,13 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
     const dim3 grid((unsigned)n_pairs * 2, (unsigned)((n_blocks + kHpTileBlocks - 1) / kHpTileBlocks));
     fb_hp_par_hist_kernel<<<n_streams, 128, 0, stream>>>(hp, hp_stride, hp_state, chunk_samples, 0, fc);
     if (pcm.channels == 2) {
-      fb_hp_par_block_kernel<2, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
+      fb_hp_par_block_kernel<2, 0><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, nullptr, sa, fc);
       fb_hp_par_scan_kernel<0><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<2, 1><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
       fb_hp_par_scan_kernel<1><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<2, 2><<<grid, 64, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
     } else {
-      fb_hp_par_block_kernel<1, 0><<<grid, 32, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sa, fc);
+      fb_hp_par_block_kernel<1, 0><<<grid, 32, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, nullptr, sa, fc);
       fb_hp_par_scan_kernel<0><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);
       fb_hp_par_block_kernel<1, 1><<<grid, 32, 0, stream>>>(d_tables, pcm, n_blocks, t0, chunk_samples, hp, hp_stride, hp_state, sa, sb, fc);
       fb_hp_par_scan_kernel<1><<<sgrid, 128, 0, stream>>>(n_streams, n_blocks, chunk_samples, hp_state, sa, sb, M, fc);

@@ -118,7 +118,7 @@ __device__ __forceinline__ void fft_pass4(double2* z, const double2* __restrict_
     const int s0 = sb ^ fft_swz(d), s1 = sb ^ fft_swz(d | LQ), s2 = sb ^ fft_swz(d | (2 * LQ)),
               s3 = sb ^ fft_swz(d | (3 * LQ));
     double2 a0 = z[s0], a1 = z[s1], a2 = z[s2], a3 = z[s3];
-    if (LQ > NT) {
+    if constexpr (LQ > NT) {
       const int k = t | (NT * (u % (LQ / NT)));
       w1 = tw[k * TS];
       w2 = cmul(w1, w1);

@@ -34,10 +34,9 @@ namespace peaq {
 namespace {
 
 constexpr double kSlopeA = 0.993355506255034;   // fbearmodel.c:49
-constexpr double kDist = 0.921851456499719;     // fbearmodel.c:50
 constexpr double kCl = 0.0802581846102741;      // fbearmodel.c:51
-constexpr double kLnDist = -0.08137117849224008;  // ln(kDist)
-constexpr double kKappa = 0.07067810761028887;    // -0.2 * 10 / ln(10) * ln(kDist)
+constexpr double kLnDist = -0.08137117849224008;  // ln DIST, DIST = 0.921851456499719 (fbearmodel.c:50)
+constexpr double kKappa = 0.07067810761028887;    // -0.2 * 10 / ln(10) * ln DIST
 enum { kStInit = 0, kStNormal = 1, kStTentative = 2 };
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -34,7 +34,7 @@ namespace peaq {
 namespace {
 
 enum { kStInit = 0, kStNormal = 1, kStTentative = 2 };
-enum { kKindSum2, kKindSum3, kKindSum2Max };   // fields (0,1) | (0,1,2) sums | (0,1) sums + field 2 maximum
+enum { kKindSum2, kKindSum2Max };   // fields (0, 1) are sums | ... and field 2 is a maximum
 
 constexpr int kMaxSeg = 512;   // segments per item the combine kernels handle (> 5 hours of audio)
 
