@@ -9,6 +9,11 @@
 namespace peaq {
 namespace {
 
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+
 #if defined(PEAQ_DEV_K2_OCC3)
 #define PEAQ_K2_MIN_CTAS 3
 #else
@@ -41,18 +46,47 @@ scan_basic_kernel(const DeviceTables* __restrict__ T, const double* __restrict__
   const unsigned total = n_frames[pair];
   const unsigned end = min(first_frame + n_chunk_frames, total);
 
+  // The three band values a thread needs from the next frame's record travel through shared
+  // memory, started one frame ahead with cp.async: every frame would otherwise begin with a DRAM
+  // round trip (the records of a chunk are far larger than L2), and a prefetch into registers
+  // costs registers this kernel does not have.  A thread reads back only what it copied itself,
+  // so no barrier is involved.  The frame's scalars (flags, bandwidths, EHS, SNR sums) are
+  // prefetched towards L1 / L2.
+  __shared__ double stage[2][3][kGroup * kMaxChannels];
+  auto stage_frame = [&](unsigned fl, int buf) {
+    const double* r = records + ((size_t)pair * n_chunk_frames + fl) * L.stride;
+    if (th.active) {
+      cp_async8(&stage[buf][0][threadIdx.x], r + (0 * C + th.c) * B + th.b);
+      cp_async8(&stage[buf][1][threadIdx.x], r + (1 * C + th.c) * B + th.b);
+      cp_async8(&stage[buf][2][threadIdx.x], r + L.off_noise + th.c * B + th.b);
+      if (th.b == 0) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(r + L.off_ehs));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(r + L.off_ints));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (first_frame < end) stage_frame(0, 0);
   for (unsigned f = first_frame; f < end; f++) {
-    const double* rec = records + ((size_t)pair * n_chunk_frames + (f - first_frame)) * L.stride;
+    const unsigned fl = f - first_frame;
+    const int buf = fl & 1;
+    const double* rec = records + ((size_t)pair * n_chunk_frames + fl) * L.stride;
     const int* rints = reinterpret_cast<const int*>(rec + L.off_ints);
+    if (f + 1 < end) {
+      stage_frame(fl + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this frame's copies have landed
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     ScanInputs in;
-    in.E2r = th.active ? rec[(0 * C + th.c) * B + th.b] : 1.;
-    in.E2t = th.active ? rec[(1 * C + th.c) * B + th.b] : 1.;
-    in.nz = th.active ? rec[L.off_noise + th.c * B + th.b] : 0.;
+    in.E2r = th.active ? stage[buf][0][threadIdx.x] : 1.;
+    in.E2t = th.active ? stage[buf][1][threadIdx.x] : 1.;
+    in.nz = th.active ? stage[buf][2][threadIdx.x] : 0.;
     in.flags = rints[0];
     in.bw = rints + 1 + 2 * th.c;
     in.ehs = rec + L.off_ehs + th.c;
     in.snr = rec + L.off_snr;
-    in.dbg = kTap ? dbg + ((size_t)pair * n_chunk_frames + (f - first_frame)) * scan_tap_doubles(C, B) : nullptr;
+    in.dbg = kTap ? dbg + ((size_t)pair * n_chunk_frames + fl) * scan_tap_doubles(C, B) : nullptr;
 #if defined(PEAQ_DEV_K2_OCC3)
     scan_step(in, MemConst{T, th.bb}, RegState{bs}, RegAcc{}, acc, cnt, sh, th, C, B);
 #else
