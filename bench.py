@@ -362,7 +362,7 @@ def pin_to_gpu_cpus(c):
     return None
 
 
-def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, what):
+def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, what, headline=False):
     """One workload (mode, pairs per GPU, item length) measured like the headline: resident steps
     with the gather inside, the end-to-end call from pinned host memory, the dominant kernel's
     roofline, the CPU sample and the parity of the GPU results against it."""
@@ -467,10 +467,17 @@ def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, wh
             each.append(round((time.perf_counter() - t1) * 1e3, 1))
         barrier(c)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_stat = "mean of the steps"
+        if not headline and e2e_steps >= 3:
+            # secondary workloads: the median step (the host side of a shared box stalls a copy now
+            # and then; every step's time is listed)
+            e2e_ms = sorted(each)[len(each) // 2]
+            e2e_stat = "median of the steps"
         e2e_ms = allmax(c, [e2e_ms])[0]
         res["e2e"] = {"value": e2e_pairs * c.world * fpp / (e2e_ms / 1e3), "unit": UNIT,
                       "h2d_bytes_per_step": 2 * hb * c.world, "d2h_bytes_per_step": e2e_pairs * c.world * 128,
-                      "ms_per_step": e2e_ms, "ms_of_each_step_rank0": each, "pairs_per_gpu": e2e_pairs,
+                      "ms_per_step": e2e_ms, "ms_per_step_is": e2e_stat, "ms_of_each_step_rank0": each,
+                      "pairs_per_gpu": e2e_pairs,
                       "steps": e2e_steps,
                       "host_memory": "pinned",
                       "bit_equal_to_resident_run": bool(np.array_equal(o2["odg"], out["odg"][:e2e_pairs], equal_nan=True))}
@@ -566,12 +573,12 @@ def our_arm(args):
     # ---- headline: BASELINE configs[1] (configs[3] at N = 8), basic ----------------------
     head, _ = measure(c, "basic", pairs_gpu, PAIR_SECONDS, args.steps, args.warmup,
                       cpu_n("basic", pairs_gpu), max(1, min(args.steps, 3)),
-                      "headline batch: first pairs of the bench workload itself")
+                      "headline batch: first pairs of the bench workload itself", headline=True)
     extra = {}
     if not args.headline_only:
         # ---- BASELINE configs[2]: advanced mode, same batch --------------------------------
         adv, _ = measure(c, "advanced", PAIRS_PER_GPU, PAIR_SECONDS, max(1, min(args.steps, 3)),
-                         min(args.warmup, 3), cpu_n("advanced", PAIRS_PER_GPU), 2,
+                         min(args.warmup, 3), cpu_n("advanced", PAIRS_PER_GPU), 3,
                          "advanced batch: first pairs of the bench workload itself")
         extra["modes"] = {"advanced": adv}
         # ---- BASELINE configs[4] shape: few long items ---------------------------------------
@@ -581,7 +588,7 @@ def our_arm(args):
             n_cpu = 0
             if not args.no_cpu_baseline and sec <= 600:
                 n_cpu = min(LONG_PAIRS_PER_GPU, cores) if single else min(LONG_PAIRS_PER_GPU, cores, 4)
-            r, _ = measure(c, mode, LONG_PAIRS_PER_GPU, sec, 3, 2, n_cpu, 1,
+            r, _ = measure(c, mode, LONG_PAIRS_PER_GPU, sec, 3, 2, n_cpu, 3 if sec <= 600 else 1,
                            "long items: first pairs of the long-item workload itself")
             long_res[mode] = r
         extra["long_items"] = long_res
