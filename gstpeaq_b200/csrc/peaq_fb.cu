@@ -917,7 +917,8 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
   // thread per stream busy for ~52 ns per sample whatever the batch, the parallel form does three
   // times the arithmetic on every SM.  Same results either way (PEAQ_B200_HP_PARALLEL=0/1 forces one).
   static const int forced = std::getenv("PEAQ_B200_HP_PARALLEL") ? std::atoi(std::getenv("PEAQ_B200_HP_PARALLEL")) : -1;
-  const bool can = chunk_samples >= 4 * kHpL && pos0 % kHpL == 0;
+  // (the block-parallel grid carries the tiles of 32 blocks in its y dimension: 65 535 x 16 384 samples)
+  const bool can = chunk_samples >= 4 * kHpL && pos0 % kHpL == 0 && chunk_samples / (kHpL * kHpTileBlocks) < 65535u;
   const bool parallel = can && (forced == 1 || (forced < 0 && n_streams <= 4096));
   if (parallel) {
     const int n_blocks = (int)((chunk_samples + kHpL - 1) / kHpL);
