@@ -207,3 +207,47 @@ def test_segment_plan_of_long_items():
             assert abs(seg / 48000. - 32.768) < 11.    # about 33 s each
     assert G.segment_plan(48000 * 600) == (18, 1600512, 196608)
     assert G.segment_plan(48000 * 3600)[0] == 110
+
+
+def test_segment_combination_rule_replayed_in_python():
+    """The rule seg_combine_* applies (peaq_segments.cu), replayed with integers: an accumulator
+    in the reference commits everything from the first frame above the threshold up to the LAST
+    one (movaccum.c:317-354: frames after it stay tentative).  Segments whose sums restart at
+    their first frame report `cur` (all their frames), `saved` (up to their own last frame above
+    the threshold, when they end tentative) and whether they own such a frame; with T = sum of
+    `cur` of the segments before s, the item's value is T + M(s) at the last owning segment."""
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n, seg = int(rng.integers(20, 200)), int(rng.integers(5, 40))
+        above = rng.random(n) < rng.choice([0.02, 0.3, 0.9])
+        above[0] = True                       # assumption A1: the item has started in segment 0
+        val = rng.integers(1, 1000, n)
+        # the sequential state machine
+        num = saved = 0
+        status = 0                            # 0 INIT, 1 NORMAL, 2 TENTATIVE
+        for f in range(n):
+            if not above[f]:
+                if status == 1:
+                    saved, status = num, 2
+            else:
+                status = 1
+            if status != 0:
+                num += int(val[f])
+        want = saved if status == 2 else num
+        # segments: status NORMAL at their start (A1), sums restart at their first frame
+        T = committed = 0
+        for s0 in range(0, n, seg):
+            cur = sv = 0
+            st, owned = 1, False
+            for f in range(s0, min(s0 + seg, n)):
+                if not above[f]:
+                    if st == 1:
+                        sv, st = cur, 2
+                else:
+                    st, owned = 1, True
+                cur += int(val[f])
+            m = sv if st == 2 else cur
+            if owned:
+                committed = T + m
+            T += cur
+        assert committed == want, (trial, n, seg)
