@@ -229,7 +229,10 @@ __device__ void spread_prepare(const DeviceTables* __restrict__ T, int B, double
 // at step t is the finished band t.  Every target still receives its terms nearest source first,
 // starting from the downward pattern, each term the same chain of products as before: results are
 // bit for bit those of the one-shuffle-per-band ladder this replaces (13 instead of 26
-// instructions per step).  On return se2[i] holds the complete spread pattern (0.4 domain).
+// instructions per step).  On return the complete spread pattern (0.4 domain) is band 0 in se2[0]
+// and band i >= 1 in scr[128 + i - 1] (spread_result).
+__device__ __forceinline__ double spread_result(const double* scr, int i) { return i ? scr[128 + i - 1] : scr[256]; }
+
 __device__ void spread_ladder(int B, double* scr, int lane) {
   const double* sa = scr;
   const double* se = scr + 128;
@@ -242,72 +245,36 @@ __device__ void spread_ladder(int B, double* scr, int lane) {
     a[m] = p < B ? sa[p] : 0.;
     acc[m] = p + 1 < B ? se2[p + 1] : 0.;
   }
-  __syncwarp();   // every lane holds its inputs: se2 may now be overwritten with finished bands
-#pragma unroll 4
-  for (int t = 1; t < B; t++) {
+  __syncwarp();   // every lane holds its inputs: se (dead from here on) receives the finished bands
+  // Four steps per trip: lane 0 keeps the four bands that finish and writes them with two 128-bit
+  // stores, band t to fin[t - 1] (the shift by one makes the groups of four 16-byte aligned; one
+  // shared-memory wavefront per two bands instead of one per band).  The last trip may run up to
+  // three steps past band B - 1: they only produce entries nobody reads (fin has 128 entries).
+  double* fin = scr + 128;
+  for (int t = 1; t < B; t += 4) {
+    double done[4];
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-      r[m] *= a[m];
-      acc[m] += r[m];
+    for (int s = 0; s < 4; s++) {
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        r[m] *= a[m];
+        acc[m] += r[m];
+      }
+      done[s] = acc[0];
+      double in = __shfl_down_sync(0xffffffffu, acc[0], 1);
+      if (lane == 31) in = 0.;
+#pragma unroll
+      for (int m = 0; m < 3; m++) acc[m] = acc[m + 1];
+      acc[3] = in;
     }
-    if (lane == 0) se2[t] = acc[0];
-    double in = __shfl_down_sync(0xffffffffu, acc[0], 1);
-    if (lane == 31) in = 0.;
-#pragma unroll
-    for (int m = 0; m < 3; m++) acc[m] = acc[m + 1];
-    acc[3] = in;
+    if (lane == 0) {
+      *reinterpret_cast<double2*>(fin + t - 1) = make_double2(done[0], done[1]);
+      *reinterpret_cast<double2*>(fin + t + 1) = make_double2(done[2], done[3]);
+    }
   }
   __syncwarp();
 }
 
-#if defined(PEAQ_DEV_OLD_LADDER)
-// round-1 ladder (development comparison): one shuffle per band and step
-__device__ void spread_ladder_r1(int B, double* scr, int lane) {
-  const double* sa = scr;
-  const double* se = scr + 128;
-  double* se2 = scr + 256;
-  double r[4], a[4], acc[4];
-#pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const int i = lane + 32 * m;
-    r[m] = i < B ? se[i] : 0.;
-    a[m] = i < B ? sa[i] : 0.;
-    acc[m] = i < B ? se2[i] : 0.;
-  }
-  auto ladder = [&](auto range, int b_begin, int b_end) {
-    constexpr int A = decltype(range)::value;   // t = 32 A + b
-    for (int b = b_begin; b < b_end; b++) {
-      const int src = (lane - b) & 31;
-      const bool same = lane >= b;
-      double v[4 - A];
-#pragma unroll
-      for (int m = 0; m < 4 - A; m++) {
-        r[m] *= a[m];
-        v[m] = __shfl_sync(0xffffffffu, r[m], src);
-      }
-#pragma unroll
-      for (int mt = A; mt < 4; mt++) {
-        const double lo = mt - A - 1 >= 0 ? v[mt - A - 1 >= 0 ? mt - A - 1 : 0] : 0.;
-        acc[mt] += same ? v[mt - A] : lo;
-      }
-    }
-  };
-  {
-    const int last = B - 1;   // largest step
-    ladder(std::integral_constant<int, 0>(), 1, last < 31 ? last + 1 : 32);
-    if (last >= 32) ladder(std::integral_constant<int, 1>(), 0, last < 63 ? last - 31 : 32);
-    if (last >= 64) ladder(std::integral_constant<int, 2>(), 0, last < 95 ? last - 63 : 32);
-    if (last >= 96) ladder(std::integral_constant<int, 3>(), 0, last - 95);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const int i = lane + 32 * m;
-    if (i < B) se2[i] = acc[m];
-  }
-  __syncwarp();
-}
-#endif
 
 // barrier of the two warps of one stream (ids 1..4), of the four warps of one channel
 // (ids 5, 6) and the arrive/wait pair that guards the ref buffer (ids 7, 8)
@@ -336,13 +303,27 @@ __device__ double ehs_channel_pair(const DeviceTables* __restrict__ T, const dou
   double2* zb = reinterpret_cast<double2*>(work) + 512;   // 256 complex (+ 129 doubles of |C|^2)
   const int sl9 = fft_slot_rt<9>(t);
   const int sl8 = fft_slot_rt<8>(t);
+  // The thread's points n = t + 64 u: for fixed parity j of u the four u = j + 2 m are the inputs
+  // of one butterfly of the first radix-4 level (top digit of n >> 1, no twiddles), which therefore
+  // runs here in registers and its outputs go where the scatter would have put the inputs.
 #pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const double v = dlog[t + 64 * u];
-    za[sl9 ^ fft_slot<9>(64 * u)] = make_double2(v, u < 4 ? v : 0.);
+  for (int j = 0; j < 2; j++) {
+    double2 a0, a1, a2, a3;
+    {
+      const double v0 = dlog[t + 64 * j], v1 = dlog[t + 64 * (j + 2)];
+      a0 = make_double2(v0, v0);
+      a1 = make_double2(v1, v1);
+      a2 = make_double2(dlog[t + 64 * (j + 4)], 0.);
+      a3 = make_double2(dlog[t + 64 * (j + 6)], 0.);
+    }
+    fft_bfly4_nt(a0, a1, a2, a3);
+    za[sl9 ^ fft_slot<9>(64 * j)] = a0;
+    za[sl9 ^ fft_slot<9>(64 * (j + 2))] = a1;
+    za[sl9 ^ fft_slot<9>(64 * (j + 4))] = a2;
+    za[sl9 ^ fft_slot<9>(64 * (j + 6))] = a3;
   }
   sync();
-  group_fft<9, 64, StreamSync>(za, tw, t, sync);
+  group_fft<9, 64, StreamSync, 4>(za, tw, t, sync);
   auto g_of = [&](int q) {
     const double2 p = za[fft_swz(q & 511)];
     const double2 m = za[fft_swz((512 - q) & 511)];
@@ -350,18 +331,23 @@ __device__ double ehs_channel_pair(const DeviceTables* __restrict__ T, const dou
     const double f2r = 0.5 * (p.y + m.y), f2i = -0.5 * (p.x - m.x);
     return make_double2((f1r * f2r + f1i * f2i) / (2 * kMaxLag), (f2r * f1i - f1r * f2i) / (2 * kMaxLag));
   };
+  // (the thread's four points k = t + 64 u are one butterfly of the first radix-4 level: registers)
+  double2 y[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     const int k = t + 64 * u;
     const double2 a = g_of(k), b = g_of(256 - k);
     const double er = a.x + b.x, ei = a.y - b.y;
     const double dr = a.x - b.x, di = a.y + b.y;
-    const double2 w = tw[2 * k];                      // e^{-2 pi i k / 512}; its conjugate is needed
+    const double2 w = tw[fft_twi(2 * t) ^ fft_twi(128 * u)];   // e^{-2 pi i k / 512}; its conjugate is needed
     const double orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
-    zb[sl8 ^ fft_slot<8>(64 * u)] = make_double2(er - oi, -(ei + orr));   // conj(E + i O)
+    y[u] = make_double2(er - oi, -(ei + orr));   // conj(E + i O)
   }
+  fft_bfly4_nt(y[0], y[1], y[2], y[3]);
+#pragma unroll
+  for (int u = 0; u < 4; u++) zb[sl8 ^ fft_slot<8>(64 * u)] = y[u];
   sync();
-  group_fft<8, 64, StreamSync>(zb, tw, t, sync);
+  group_fft<8, 64, StreamSync, 4>(zb, tw, t, sync);
   // thread owns lags i = 4 t .. 4 t + 3: c[2m] = Re, c[2m+1] = -Im of element m = 2 t + p
   double c[4];
 #pragma unroll
@@ -489,7 +475,7 @@ __device__ __forceinline__ void refbuf_wait(int chan) {
 __device__ __forceinline__ void frame_load_twiddles(const DeviceTables* __restrict__ T, double* smem) {
   double2* tw = reinterpret_cast<double2*>(smem);   // 512 complex
   for (int i = threadIdx.x; i < 512; i += blockDim.x)
-    tw[i] = make_double2(T->tw1024[i].x, T->tw1024[i].y);
+    tw[fft_twi(i)] = make_double2(T->tw1024[i].x, T->tw1024[i].y);   // swizzled table (peaq_fft.cuh)
 }
 
 // Whole frame inside both signals and 16-byte aligned: it is staged with two TMA bulk copies
@@ -657,21 +643,41 @@ __device__ __forceinline__ void frame_body(const DeviceTables* __restrict__ T, c
   __syncthreads();   // twiddles loaded, mail published, scatter of both halves complete
 
   // ---- 2048-point real FFT by the stream's 64 threads; power spectrum into registers ----
-  FftPasses<10, 4, 64, StreamSync>::run(z, tw, t, StreamSync{1 + stream});   // passes 2..5
+  // Levels 4 + 16 in one trip through shared memory, levels 64 + 256 in a second one that ends in
+  // registers (peaq_fft.cuh): thread t then holds Z[t + 64 u], u < 16.
   // Z[k] and Z[1024-k] give X[k] = E + P and X[1024-k] = conj(E - P) (E, O the even/odd parts,
-  // P = O w^k), so one pair of loads and one twiddle product serve two bins: register u < 8
+  // P = O w^k), so one pair of values and one twiddle product serve two bins: register u < 8
   // holds bin t + 64 u, register 8 + u its mirror 1024 - (t + 64 u); bin 512 (its own mirror)
-  // is an extra of thread 0.
+  // is an extra of thread 0.  Z[k], k = t + 64 u < 512, is the thread's own e[u]; the mirror
+  // Z[1024 - k] = Z[(64 - t) + 64 (15 - u)] is e[15 - u] of thread 64 - t, so only the upper
+  // halves e[8..15] go through shared memory once more: row u - 8, column (t - 1) & 63 of a plain
+  // 8 x 64 exchange array (consecutive lanes, consecutive 16-byte slots, for the store and for the
+  // mirrored load alike).  Thread 0 is its own partner, one register further up: Z[1024 - 64 u] =
+  // its e[16 - u] (row 8 - u), and Z[0] mirrors itself.
+  const StreamSync ssync{1 + stream};
+  fft1024_levels_4_16(z, tw, t);
+  ssync();
   double pv[16], p_mid = 0.;
   auto bin_of = [&](int u) { return u < 8 ? t + 64 * u : 1024 - (t + 64 * (u - 8)); };
   {
     const double lf = T->level_factor_fft;
-    const int sw = fft_swz(t);
+    double2 e[16];
+    fft1024_load_64_256(e, z, t);
+    ssync();   // every thread holds its sixteen inputs: the buffer becomes the exchange array
+    double2* xch = z;
+    fft1024_levels_64_256(e, xch, tw, t);
+    if (t == 0) {
+      const double2 p = xch[fft1024_xch_mid()];   // Z[512]: E = (Re, 0), O = (Im, 0), w^512 = -i
+      const double wr = T->tw2048[512].x, wi = T->tw2048[512].y;
+      const double xr = p.x + p.y * wr, xi = p.y * wi;
+      p_mid = (xr * xr + xi * xi) * lf;
+    }
+    ssync();
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       const int k = t + 64 * u;
-      const double2 p = z[sw ^ fft_swz(64 * u)];
-      const double2 q = z[fft_swz((1024 - k) & 1023)];
+      const double2 p = e[u];
+      const double2 q = fft1024_mirror(xch, t, u, p);
       const double er = 0.5 * (p.x + q.x), ei = 0.5 * (p.y - q.y);
       const double orr = 0.5 * (p.y + q.y), oi = -0.5 * (p.x - q.x);
       const double wr = T->tw2048[k].x, wi = T->tw2048[k].y;
@@ -680,12 +686,6 @@ __device__ __forceinline__ void frame_body(const DeviceTables* __restrict__ T, c
       const double yr = er - pr, yi = ei - pi;
       pv[u] = (xr * xr + xi * xi) * lf;   // fftearmodel.c:464-466
       pv[8 + u] = (yr * yr + yi * yi) * lf;
-    }
-    if (t == 0) {
-      const double2 p = z[fft_swz(512)];   // E = (Re, 0), O = (Im, 0), w^512 = -i
-      const double wr = T->tw2048[512].x, wi = T->tw2048[512].y;
-      const double xr = p.x + p.y * wr, xi = p.y * wi;
-      p_mid = (xr * xr + xi * xi) * lf;
     }
   }
 
@@ -777,16 +777,11 @@ __device__ __forceinline__ void frame_body(const DeviceTables* __restrict__ T, c
     if (!skip) {
       __syncwarp();
       spread_prepare(T, B, scratch, se, scratch + 256, lane);
-#if defined(PEAQ_DEV_OLD_LADDER)
-      spread_ladder_r1(B, scratch, lane);
-#else
       spread_ladder(B, scratch, lane);
-#endif
       // E2 = E2s^(1/0.4) / norm  (:673-675); x^2.5 = x^2 sqrt(x)
-      const double* fin = scratch + 256;
       double* out = kFused ? const_cast<double*>(frame_out_e2(smem, chan, role)) : rec + (role * C + chan) * B;
       for (int i = lane; i < B; i += 32) {
-        const double v = fin[i];
+        const double v = spread_result(scratch, i);
         out[i] = v * v * sqrt(v) / T->spread_norm[i];
       }
     }

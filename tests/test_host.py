@@ -251,3 +251,19 @@ def test_segment_combination_rule_replayed_in_python():
                 committed = T + m
             T += cur
         assert committed == want, (trial, n, seg)
+
+
+def test_frame_kernel_fft_two_trip_form_replayed_on_the_host(tmp_path):
+    """The 1024-point transform of the frame kernel (peaq_fft.cuh: two radix-4 levels per trip through
+    shared memory, mirror exchange, swizzled twiddle table) and the register-resident first levels of
+    the EHS transforms, run thread by thread on the host: bit-equal to the single-level passes, equal
+    to a long-double DFT, every 128-bit shared-memory access at its minimum wavefront count."""
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "fft_check")
+    subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-fmad=false", "-w", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "fft_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
