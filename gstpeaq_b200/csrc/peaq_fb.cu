@@ -31,6 +31,8 @@
 #include "peaq_engine.h"
 
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace peaq {
 namespace {
@@ -685,16 +687,38 @@ __device__ __forceinline__ void load6(const double* __restrict__ px, double (&x)
   }
 }
 
+// Coefficients of the recursions in CONSTANT memory: P_f[k] of every band, [band][k][f] (61 440
+// bytes), and -e^{j w N} per band.  The inner loop reads them with warp-uniform addresses, i.e.
+// through the uniform datapath (SASS: LDCU.64 UR, c[0x3][UR+imm]; DFMA R, R, UR, R) instead of the
+// shared-memory pipe.  That pipe was what bound this kernel (88 % of its wavefront rate, FP64
+// pipe 64 %, profiles/r2_fb_bank_rec_ncu.txt): a broadcast 128-bit shared load costs four
+// wavefronts like any other, so per tap index k the three coefficients cost as much as the lane's
+// six samples (12 + 12..16 wavefronts against 18 cycles of DFMAs).  The table of the leaving side,
+// Q_f[k] = -e^{j w N} P_f[k], would not fit next to P (64 KB of constant memory): the leaving
+// samples are accumulated with P first and the sums multiplied by -e^{j w N} once per group.
+// The tables are model constants (no playback level in them): one copy per device.
+__constant__ double2 c_fb_rec_p[kFbRecBands * 32 * 3];
+__constant__ double2 c_fb_rec_me[kFbRecBands];
+
 // acc[f][i] += coef[3 k + f] * px[i] for k in [k0, k1), px moving up one row (one sample
-// back in time) per k
-template <bool kOdd>
+// back in time) per k.  kConst: coef = c_fb_rec_p + cbase, else the shared-memory copy `coef`.
+template <bool kOdd, bool kConst>
 __device__ __forceinline__ void rec_accumulate(double2 (&acc)[3][kFbRecGroup], const double* __restrict__ px,
-                                               const double2* __restrict__ coef, int k0, int k1) {
+                                               const double2* __restrict__ coef, int cbase, int k0, int k1) {
 #pragma unroll 2
   for (int k = k0; k < k1; k++) {
     double x[kFbRecGroup];
     load6<kOdd>(px, x);
-    const double2 c0 = coef[3 * k], c1 = coef[3 * k + 1], c2 = coef[3 * k + 2];
+    double2 c0, c1, c2;
+    if (kConst) {
+      c0 = c_fb_rec_p[cbase + 3 * k];
+      c1 = c_fb_rec_p[cbase + 3 * k + 1];
+      c2 = c_fb_rec_p[cbase + 3 * k + 2];
+    } else {
+      c0 = coef[3 * k];
+      c1 = coef[3 * k + 1];
+      c2 = coef[3 * k + 2];
+    }
 #pragma unroll
     for (int i = 0; i < kFbRecGroup; i++) {
       acc[0][i].x = fma(c0.x, x[i], acc[0][i].x);
@@ -712,17 +736,18 @@ __device__ __forceinline__ void rec_accumulate(double2 (&acc)[3][kFbRecGroup], c
 // x[32 s - a] sits in row (-a) mod 32, column s - ceil(a / 32) - mbase: the row falls by one
 // per k and wraps once, where the column steps back and (the row pitch being even) the
 // 16-byte alignment of the lane's six columns flips.
+template <bool kConst>
 __device__ __forceinline__ void rec_side(double2 (&acc)[3][kFbRecGroup], const double* __restrict__ col0, int a0,
-                                         const double2* __restrict__ coef) {
+                                         const double2* __restrict__ coef, int cbase) {
   const int row = (-a0) & 31, q = (a0 + 31) >> 5;
   const int k1 = row + 1;   // k < k1: before the wrap
   const double* __restrict__ px = col0 + row * kRecStride - q;
   if (reinterpret_cast<uintptr_t>(px) & 8) {
-    rec_accumulate<true>(acc, px, coef, 0, k1);
-    rec_accumulate<false>(acc, col0 + 31 * kRecStride - (q + 1), coef, k1, 32);
+    rec_accumulate<true, kConst>(acc, px, coef, cbase, 0, k1);
+    rec_accumulate<false, kConst>(acc, col0 + 31 * kRecStride - (q + 1), coef, cbase, k1, 32);
   } else {
-    rec_accumulate<false>(acc, px, coef, 0, k1);
-    rec_accumulate<true>(acc, col0 + 31 * kRecStride - (q + 1), coef, k1, 32);
+    rec_accumulate<false, kConst>(acc, px, coef, cbase, 0, k1);
+    rec_accumulate<true, kConst>(acc, col0 + 31 * kRecStride - (q + 1), coef, cbase, k1, 32);
   }
 }
 
@@ -731,6 +756,7 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
                : "memory");
 }
 
+template <bool kConst>
 __global__ void __launch_bounds__(32 * kRecWarps, 2)
 fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp, size_t hp_stride,
                    unsigned n_sub /* sub-steps in this chunk, a multiple of 6 */, double2* __restrict__ fbout,
@@ -783,10 +809,12 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
     const int n_groups = min(32, (int)(n_sub - S0) / kFbRecGroup);
     const double* __restrict__ col0 = xs + kFbRecGroup * lane + kRecHistRows;   // column of x[32 s0 - 0]
     for (int slot = 0; slot < n_slots; slot++) {
-      const int b = warp + kRecWarps * slot;
-      const int N = T->fb_len[b];
+      // (broadcasts from lane 0: tells the compiler that band and length are the same for the whole
+      // warp, which puts the coefficient addresses and the loop counters on the uniform datapath)
+      const int b = __shfl_sync(0xffffffffu, warp + kRecWarps * slot, 0);
+      const int N = __shfl_sync(0xffffffffu, T->fb_len[b], 0);
       const int D = 1 + (kFbBuf - N) / 2;
-      {
+      if (!kConst) {
         const double2* __restrict__ ph = reinterpret_cast<const double2*>(&T->fb_rec_ph[b][0][0]);
         // [side][k][f] in shared memory
 #pragma unroll
@@ -802,8 +830,19 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
       for (int f = 0; f < 3; f++)
 #pragma unroll
         for (int i = 0; i < kFbRecGroup; i++) acc[f][i] = make_double2(0., 0.);
-      rec_side(acc, col0, D, phs);            // the 32 samples that entered the window
-      rec_side(acc, col0, D + N, phs + 96);   // the 32 that left it
+      if (kConst) {
+        rec_side<true>(acc, col0, D + N, nullptr, b * 96);   // the 32 samples that left the window, with P ...
+        const double2 me = c_fb_rec_me[b];                   // ... times -e^{j w N} = their Q
+#pragma unroll
+        for (int f = 0; f < 3; f++)
+#pragma unroll
+          for (int i = 0; i < kFbRecGroup; i++)
+            acc[f][i] = make_double2(fma(acc[f][i].x, me.x, -(acc[f][i].y * me.y)), fma(acc[f][i].x, me.y, acc[f][i].y * me.x));
+        rec_side<true>(acc, col0, D, nullptr, b * 96);       // the 32 that entered it
+      } else {
+        rec_side<false>(acc, col0, D, phs, 0);            // the 32 samples that entered the window
+        rec_side<false>(acc, col0, D + N, phs + 96, 0);   // the 32 that left it
+      }
       // zero-state response of the group, P[i] = r P[i-1] + W[i]; group totals to the chain lanes
       const double2* __restrict__ rp = reinterpret_cast<const double2*>(&T->fb_rec_rpow[b][0][0]);
 #pragma unroll
@@ -963,6 +1002,30 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
   return cudaGetLastError();
 }
 
+// The recursion coefficients into the constant memory of the current device, once per device and
+// process (they are the same for every engine: nothing in them depends on the playback level).
+static cudaError_t fb_bank_upload_constants(const DeviceTables* h_tables) {
+  static std::mutex mu;
+  static bool done[256] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 256 && done[dev]) return cudaSuccess;
+  std::vector<double2> p((size_t)kFbRecBands * 96), me(kFbRecBands);
+  for (int b = 0; b < kFbRecBands; b++) {
+    for (int k = 0; k < 32; k++)
+      for (int f = 0; f < 3; f++) p[(size_t)b * 96 + 3 * k + f] = make_double2(h_tables->fb_rec_ph[b][k][f].x, h_tables->fb_rec_ph[b][k][f].y);
+    me[b] = make_double2(h_tables->fb_rec_me[b].x, h_tables->fb_rec_me[b].y);
+  }
+  e = cudaMemcpyToSymbol(c_fb_rec_p, p.data(), p.size() * sizeof(double2));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(c_fb_rec_me, me.data(), me.size() * sizeof(double2));
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 256) done[dev] = true;
+  return cudaSuccess;
+}
+
 cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_tables,
                            const double* hp, size_t hp_stride, int n_streams, unsigned n_sub,
                            double* fbout, double* hp_state, bool first_chunk, bool direct_only,
@@ -973,10 +1036,23 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
   // polyphase direct FIRs (cross-check)
   if (!direct_only) {
     cudaError_t e;
+    // PEAQ_B200_FB_SMEM_COEF=1: coefficients from shared memory (both sides from the tables), the
+    // form this kernel had before the constant-memory tables
+    static const bool smem_coef = std::getenv("PEAQ_B200_FB_SMEM_COEF") && std::atoi(std::getenv("PEAQ_B200_FB_SMEM_COEF"));
     const size_t smem_rec = sizeof(double) * kRecXsDoubles + sizeof(double2) * (96 + 3 * kRecSlots + 192) * kRecWarps;
-    e = cudaFuncSetAttribute(fb_bank_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+    if (smem_coef) {
+      e = cudaFuncSetAttribute(fb_bank_rec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+      if (e != cudaSuccess) return e;
+      fb_bank_rec_kernel<false><<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
+          d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
+          first_chunk ? 1 : 0, n_frames, first_frame, streams_per_pair);
+      return cudaGetLastError();
+    }
+    e = fb_bank_upload_constants(h_tables);
     if (e != cudaSuccess) return e;
-    fb_bank_rec_kernel<<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
+    e = cudaFuncSetAttribute(fb_bank_rec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+    if (e != cudaSuccess) return e;
+    fb_bank_rec_kernel<true><<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
         d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
         first_chunk ? 1 : 0, n_frames, first_frame, streams_per_pair);
     return cudaGetLastError();
