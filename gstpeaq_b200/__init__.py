@@ -202,9 +202,9 @@ def table(advanced, model, which, playback_level=92.0):
 
 def fb_filter_tables(band, playback_level=92.0):
     """Filter-bank tables of one band (host code): dict with N, D, the recursion coefficients
-    ph[k, 6] = {P_0, P_+, P_-, Q_0, Q_+, Q_-}[k], rotations rpow[f, i] = e^{j 32 w_f (i+1)} and
-    me = -e^{j w N} (Q = me P) of fb_bank_rec_kernel, and the reference-form taps h[0..N/2] (fbearmodel.c:213-220)."""
-    buf = np.zeros(1882, dtype=np.float64)
+    ph[k, 6] = {P_0, P_+, P_-, Q_0, Q_+, Q_-}[k] and rotations rpow[f, i] = e^{j 32 w_f (i+1)} of
+    fb_bank_rec_kernel, and the reference-form taps h[0..N/2] (fbearmodel.c:213-220)."""
+    buf = np.zeros(1880, dtype=np.float64)
     n = load_library().peaq_b200_table(1, float(playback_level), 2, int(band), buf.ctypes.data)
     if n < 0:
         _check(n)
@@ -214,12 +214,10 @@ def fb_filter_tables(band, playback_level=92.0):
     o += 384
     rp = buf[o:o + 36].reshape(3, 6, 2)
     o += 36
-    me = complex(buf[o], buf[o + 1])   # -e^{j w N}: Q_f[k] = me P_f[k]
-    o += 2
     hre = buf[o:o + N // 2 + 1]
     him = buf[o + N // 2 + 1:o + 2 * (N // 2 + 1)]
     return {"N": N, "D": D, "ph": ph[..., 0] + 1j * ph[..., 1], "rpow": rp[..., 0] + 1j * rp[..., 1],
-            "me": me, "h": hre + 1j * him}
+            "h": hre + 1j * him}
 
 
 class DeviceBuffer:

@@ -1708,8 +1708,8 @@ int peaq_b200_table(int advanced, double playback_level, int model, int which, d
   const DeviceTables& t = *tp;
   if (model == 2) {
     // filter-bank tables of band `which`: N, D, the recursion coefficients [32][6] complex and
-    // rotations [3][6] complex and -e^{j w N} (fb_bank_rec_kernel), then the reference-form taps
-    // re[0..N/2], im[0..N/2] (fbearmodel.c:213-220) -- up to 1882 doubles
+    // rotations [3][6] complex (fb_bank_rec_kernel), then the reference-form taps re[0..N/2],
+    // im[0..N/2] (fbearmodel.c:213-220) -- up to 1880 doubles
     if (which < 0 || which >= kFbBands) return fail(PEAQ_B200_ERR_INVALID, "no such band");
     const int N = t.fb_len[which];
     int n = 0;
@@ -1726,8 +1726,6 @@ int peaq_b200_table(int advanced, double playback_level, int model, int which, d
           out[n++] = t.fb_rec_rpow[which][f][i].x;
           out[n++] = t.fb_rec_rpow[which][f][i].y;
         }
-      out[n++] = t.fb_rec_me[which].x;
-      out[n++] = t.fb_rec_me[which].y;
     }
     for (int i = 0; i <= N / 2; i++) out[n++] = t.fb_h_re[t.fb_tap_offset[which] + i];
     for (int i = 0; i <= N / 2; i++) out[n++] = t.fb_h_im[t.fb_tap_offset[which] + i];

@@ -687,18 +687,19 @@ __device__ __forceinline__ void load6(const double* __restrict__ px, double (&x)
   }
 }
 
-// Coefficients of the recursions in CONSTANT memory: P_f[k] of every band, [band][k][f] (61 440
-// bytes), and -e^{j w N} per band.  The inner loop reads them with warp-uniform addresses, i.e.
-// through the uniform datapath (SASS: LDCU.64 UR, c[0x3][UR+imm]; DFMA R, R, UR, R) instead of the
-// shared-memory pipe.  That pipe was what bound this kernel (88 % of its wavefront rate, FP64
-// pipe 64 %, profiles/r2_fb_bank_rec_ncu.txt): a broadcast 128-bit shared load costs four
-// wavefronts like any other, so per tap index k the three coefficients cost as much as the lane's
-// six samples (12 + 12..16 wavefronts against 18 cycles of DFMAs).  The table of the leaving side,
-// Q_f[k] = -e^{j w N} P_f[k], would not fit next to P (64 KB of constant memory): the leaving
-// samples are accumulated with P first and the sums multiplied by -e^{j w N} once per group.
-// The tables are model constants (no playback level in them): one copy per device.
+// Coefficients of the ENTERING side in constant memory: P_f[k] of every band, [band][k][f]
+// (61 440 bytes).  The inner loop reads them with warp-uniform addresses, i.e. through the uniform
+// datapath (SASS: LDCU.64 UR, c[0x3][UR+imm]; DFMA R, R, UR, R), not through the shared-memory
+// pipe.  That pipe bounded this kernel (88 % of its wavefront rate against 64 % of the FP64 pipe,
+// profiles/r2_fb_bank_rec_ncu.txt): a broadcast 128-bit shared load costs four wavefronts like any
+// other, so per tap index k the three coefficients cost as much as the lane's six samples
+// (12 + 12..16 wavefronts against 18 cycles of DFMAs).  The constant path has a limit of its own
+// -- with BOTH sides on it the loop stalls on the constant loads instead (MIO throttle, measured:
+// 362.5 ms per 4096 pairs against 364.0 from shared memory) -- so the load is split: entering side
+// from constant memory, leaving side (Q_f[k]) from the warp's shared-memory copy as before:
+// 330.3 ms, the same bits.  The table is a model constant (no playback level in it): one copy per
+// device.
 __constant__ double2 c_fb_rec_p[kFbRecBands * 32 * 3];
-__constant__ double2 c_fb_rec_me[kFbRecBands];
 
 // acc[f][i] += coef[3 k + f] * px[i] for k in [k0, k1), px moving up one row (one sample
 // back in time) per k.  kConst: coef = c_fb_rec_p + cbase, else the shared-memory copy `coef`.
@@ -756,7 +757,7 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
                : "memory");
 }
 
-template <bool kConst>
+template <bool kConstP>   // entering side's coefficients from constant memory (default) or, like the leaving side's, from shared memory
 __global__ void __launch_bounds__(32 * kRecWarps, 2)
 fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict__ hp, size_t hp_stride,
                    unsigned n_sub /* sub-steps in this chunk, a multiple of 6 */, double2* __restrict__ fbout,
@@ -814,14 +815,24 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
       const int b = __shfl_sync(0xffffffffu, warp + kRecWarps * slot, 0);
       const int N = __shfl_sync(0xffffffffu, T->fb_len[b], 0);
       const int D = 1 + (kFbBuf - N) / 2;
-      if (!kConst) {
+      {
+        // this band's coefficients [side][k][f] into the warp's shared-memory copy (kConstP: the
+        // leaving side only)
         const double2* __restrict__ ph = reinterpret_cast<const double2*>(&T->fb_rec_ph[b][0][0]);
-        // [side][k][f] in shared memory
+        if (kConstP) {
 #pragma unroll
-        for (int u = 0; u < 6; u++) {
-          const int e = lane + 32 * u;          // = 6 k + side * 3 + f
-          const int k = e / 6, r = e - 6 * k;
-          phs[(r >= 3 ? 96 : 0) + 3 * k + (r >= 3 ? r - 3 : r)] = __ldg(ph + e);
+          for (int u = 0; u < 3; u++) {
+            const int e = lane + 32 * u;          // = 3 k + f
+            const int k = e / 3, f = e - 3 * k;
+            phs[96 + e] = __ldg(ph + 6 * k + 3 + f);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 6; u++) {
+            const int e = lane + 32 * u;          // = 6 k + side * 3 + f
+            const int k = e / 6, r = e - 6 * k;
+            phs[(r >= 3 ? 96 : 0) + 3 * k + (r >= 3 ? r - 3 : r)] = __ldg(ph + e);
+          }
         }
         __syncwarp();
       }
@@ -830,19 +841,8 @@ fb_bank_rec_kernel(const DeviceTables* __restrict__ T, const double* __restrict_
       for (int f = 0; f < 3; f++)
 #pragma unroll
         for (int i = 0; i < kFbRecGroup; i++) acc[f][i] = make_double2(0., 0.);
-      if (kConst) {
-        rec_side<true>(acc, col0, D + N, nullptr, b * 96);   // the 32 samples that left the window, with P ...
-        const double2 me = c_fb_rec_me[b];                   // ... times -e^{j w N} = their Q
-#pragma unroll
-        for (int f = 0; f < 3; f++)
-#pragma unroll
-          for (int i = 0; i < kFbRecGroup; i++)
-            acc[f][i] = make_double2(fma(acc[f][i].x, me.x, -(acc[f][i].y * me.y)), fma(acc[f][i].x, me.y, acc[f][i].y * me.x));
-        rec_side<true>(acc, col0, D, nullptr, b * 96);       // the 32 that entered it
-      } else {
-        rec_side<false>(acc, col0, D, phs, 0);            // the 32 samples that entered the window
-        rec_side<false>(acc, col0, D + N, phs + 96, 0);   // the 32 that left it
-      }
+      rec_side<kConstP>(acc, col0, D, phs, b * 96);       // the 32 samples that entered the window
+      rec_side<false>(acc, col0, D + N, phs + 96, 0);     // the 32 that left it
       // zero-state response of the group, P[i] = r P[i-1] + W[i]; group totals to the chain lanes
       const double2* __restrict__ rp = reinterpret_cast<const double2*>(&T->fb_rec_rpow[b][0][0]);
 #pragma unroll
@@ -1002,7 +1002,7 @@ cudaError_t launch_fb_hp(const DeviceTables* d_tables, PcmView pcm, int n_pairs,
   return cudaGetLastError();
 }
 
-// The recursion coefficients into the constant memory of the current device, once per device and
+// The entering side's recursion coefficients into the constant memory of the current device, once per device and
 // process (they are the same for every engine: nothing in them depends on the playback level).
 static cudaError_t fb_bank_upload_constants(const DeviceTables* h_tables) {
   static std::mutex mu;
@@ -1012,15 +1012,11 @@ static cudaError_t fb_bank_upload_constants(const DeviceTables* h_tables) {
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lock(mu);
   if (dev >= 0 && dev < 256 && done[dev]) return cudaSuccess;
-  std::vector<double2> p((size_t)kFbRecBands * 96), me(kFbRecBands);
-  for (int b = 0; b < kFbRecBands; b++) {
+  std::vector<double2> p((size_t)kFbRecBands * 96);
+  for (int b = 0; b < kFbRecBands; b++)
     for (int k = 0; k < 32; k++)
       for (int f = 0; f < 3; f++) p[(size_t)b * 96 + 3 * k + f] = make_double2(h_tables->fb_rec_ph[b][k][f].x, h_tables->fb_rec_ph[b][k][f].y);
-    me[b] = make_double2(h_tables->fb_rec_me[b].x, h_tables->fb_rec_me[b].y);
-  }
   e = cudaMemcpyToSymbol(c_fb_rec_p, p.data(), p.size() * sizeof(double2));
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpyToSymbol(c_fb_rec_me, me.data(), me.size() * sizeof(double2));
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 256) done[dev] = true;
   return cudaSuccess;
@@ -1036,23 +1032,18 @@ cudaError_t launch_fb_bank(const DeviceTables* d_tables, const DeviceTables* h_t
   // polyphase direct FIRs (cross-check)
   if (!direct_only) {
     cudaError_t e;
-    // PEAQ_B200_FB_SMEM_COEF=1: coefficients from shared memory (both sides from the tables), the
-    // form this kernel had before the constant-memory tables
+    // PEAQ_B200_FB_SMEM_COEF=1: both sides' coefficients from shared memory (the kernel's earlier
+    // form; same results bit for bit)
     static const bool smem_coef = std::getenv("PEAQ_B200_FB_SMEM_COEF") && std::atoi(std::getenv("PEAQ_B200_FB_SMEM_COEF"));
     const size_t smem_rec = sizeof(double) * kRecXsDoubles + sizeof(double2) * (96 + 3 * kRecSlots + 192) * kRecWarps;
-    if (smem_coef) {
-      e = cudaFuncSetAttribute(fb_bank_rec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+    auto kernel = smem_coef ? fb_bank_rec_kernel<false> : fb_bank_rec_kernel<true>;
+    if (!smem_coef) {
+      e = fb_bank_upload_constants(h_tables);
       if (e != cudaSuccess) return e;
-      fb_bank_rec_kernel<false><<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
-          d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
-          first_chunk ? 1 : 0, n_frames, first_frame, streams_per_pair);
-      return cudaGetLastError();
     }
-    e = fb_bank_upload_constants(h_tables);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_bank_rec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
-    if (e != cudaSuccess) return e;
-    fb_bank_rec_kernel<true><<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
+    kernel<<<(unsigned)n_streams, 32 * kRecWarps, smem_rec, stream>>>(
         d_tables, hp, hp_stride, n_sub, reinterpret_cast<double2*>(fbout), (size_t)kFbBands * n_sub, hp_state,
         first_chunk ? 1 : 0, n_frames, first_frame, streams_per_pair);
     return cudaGetLastError();

@@ -208,8 +208,6 @@ void fill_fb_model(DeviceTables* t, double playback_level) {
     const long double wf[3] = {w, w + d, w - d};
     const long double gain[3] = {2.L, -1.L, -1.L};
     const long double amp = (long double)ear_weight(fc[band]) / N;
-    t->fb_rec_me[band].x = (double)(-cosl(w * N));
-    t->fb_rec_me[band].y = (double)(-sinl(w * N));
     for (int f = 0; f < 3; f++) {
       for (int k = 0; k < 32; k++) {
         // g_f e^{j w_f k} with g_f = gain_f amp e^{-j w N / 2}

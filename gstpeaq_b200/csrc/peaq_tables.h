@@ -88,7 +88,6 @@ struct DeviceTables {
   // fb_rec_rpow[b][f][i] = e^{j 32 w_f (i + 1)}, i < 6
   alignas(16) double2_t fb_rec_ph[kFbRecBands][32][6];
   alignas(16) double2_t fb_rec_rpow[kFbRecBands][3][kFbRecGroup];
-  alignas(16) double2_t fb_rec_me[kFbRecBands];   // -e^{j w N}: Q_f[k] = fb_rec_me * P_f[k]
   double2_t fb_rec_alias;           // band 0: tap at delay 1456, which the reference reads from the newest sample
   // neural network (nn.c:40-93)
   double nn_amin[11], nn_amax[11];

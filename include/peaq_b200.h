@@ -135,8 +135,8 @@ int peaq_b200_engine_copy_fb_debug(peaq_b200_engine *e, double *dst, size_t max_
 /* constant tables of the engine for a mode / playback level (host code, no
  * GPU needed; same `model`/`which` numbering as the oracle's
  * peaq_oracle_table); returns the count, < 0 on error.  model 2: the filter-bank
- * tables of band `which` -- N, D, recursion coefficients [32][6], rotations [3][6] and -e^{jwN}
- * (complex), then the taps re[0..N/2], im[0..N/2]; `out` must hold 1882 doubles */
+ * tables of band `which` -- N, D, recursion coefficients [32][6] and rotations [3][6]
+ * (complex), then the taps re[0..N/2], im[0..N/2]; `out` must hold 1880 doubles */
 int peaq_b200_table(int advanced, double playback_level, int model, int which, double *out);
 /* How a batch item of n_samples per channel is run (host code, no GPU needed): the number of
  * segments it is cut into (1: not cut), their length and the warm-up every segment after the

@@ -108,9 +108,6 @@ def test_filter_bank_recursion_tables_reproduce_the_taps():
         c = -ph[:, 3:] / ph[:, :3]
         np.testing.assert_allclose(np.abs(c), 1.0, rtol=0, atol=1e-13)
         np.testing.assert_allclose(c, c[1, 0], rtol=0, atol=1e-12)
-        # ... which the kernel applies as one factor per band: Q = me P to the last bit or so
-        np.testing.assert_allclose(ph[:, 3:], t["me"] * ph[:, :3], rtol=0, atol=1e-15 * scale)
-        assert abs(abs(t["me"]) - 1.0) < 1e-15
         # rotations: |r| = 1, r_f^(i+1); and P_f[k+1] / P_f[k] = e^{j w_f} = r_f^(1/32)
         np.testing.assert_allclose(np.abs(rp), 1.0, rtol=0, atol=1e-15)
         for f in range(3):
@@ -143,8 +140,7 @@ def test_filter_bank_recursion_equals_direct_fir_in_numpy():
         worst, scale = 0.0, 0.0
         for s in range(n_sub):
             direct = np.sum(h[n] * at(32 * s - D - n))
-            # the leaving samples with P, times -e^{jwN}, then the entering ones (the kernel's order)
-            S = rp[:, 0] * S + (t["me"] * (ph[:, :3].T @ at(32 * s - D - k - N)) + ph[:, :3].T @ at(32 * s - D - k))
+            S = rp[:, 0] * S + ph[:, :3].T @ at(32 * s - D - k) + ph[:, 3:].T @ at(32 * s - D - k - N)
             worst = max(worst, abs(S.sum() - direct))
             scale = max(scale, abs(direct))
         assert worst < 1e-12 * scale, (band, worst, scale)
