@@ -9,7 +9,8 @@
 //   FB2 fb_bank_rec_kernel  the 40 complex FIR filters of 52..1456 taps, evaluated every
 //                         32 samples (apply_filter_bank, fbearmodel.c:398-435), as
 //                         sliding windowed DFTs: 384 FMAs per band and sub-step whatever
-//                         the filter length (see the comment at the kernel)
+//                         the filter length (see the comment at the kernel); half of its
+//                         coefficients come from constant memory through the uniform datapath
 //       fb_bank_kernel    the same filters as polyphase direct FIRs (2 (N - 1) FMAs per
 //                         band and sub-step); the engine's cross-check, selected with
 //                         PEAQ_B200_FB_DIRECT=1 (tests/test_gpu_parity.py compares the two)

@@ -1,20 +1,26 @@
-// Warp-level double-precision FFT in shared memory (sm_100a).
+// Double-precision FFTs in shared memory for the frame kernel (sm_100a).
 //
-// One warp transforms N = 2^LOG2N complex points held in shared memory:
-// in-place radix-4 decimation in time (plus one radix-2 pass when LOG2N is
-// odd).  The caller stores input sample n at slot fft_slot<LOG2N>(n) (base-4
-// digit reversal, XOR-swizzled); the result is in natural order behind the
-// same swizzle: X[k] = z[fft_swz(k)].
+// A group of NT threads (one warp, or the two warps of a stream) transforms N = 2^LOG2N complex
+// points held in shared memory: in-place radix-4 decimation in time (plus one radix-2 pass when
+// LOG2N is odd).  The caller stores input sample n at slot fft_slot<LOG2N>(n) (base-4 digit
+// reversal, XOR-swizzled); the result is in natural order behind the same swizzle:
+// X[k] = z[fft_swz(k)].  Two forms:
+//   * fft_pass4 / group_fft / warp_fft: one radix-4 level per trip through shared memory (the EHS
+//     transforms of 512, 256 and 128 points; their first level runs in the caller's registers);
+//   * fft1024_*: the 1024-point transform of the frame's spectrum, TWO levels per trip, ending in
+//     registers, the mirror values of the real-FFT split exchanged through a plain 8 x 64 array.
 //
-// The swizzle folds index bits 3,4,6,8,9 into the low three bits so that every
-// 128-bit shared-memory access of every pass, the digit-reversed input scatter
-// and the natural-order read-out are bank-conflict free for N = 1024.  It is
-// linear over GF(2) (swz(a ^ b) = swz(a) ^ swz(b)) and every index used by a
-// pass is lane_part ^ compile_time_part with disjoint bits, so a pass computes
-// ONE swizzle per lane; all other addresses are XORs with constants.
+// The swizzle folds index bits 3,4,6,8,9 into the low three bits so that every 128-bit
+// shared-memory access of every pass, the digit-reversed input scatter and the natural-order
+// read-out are bank-conflict free for N = 1024.  It is linear over GF(2) (swz(a ^ b) = swz(a) ^
+// swz(b)) and every index used by a pass is lane_part ^ compile_time_part with disjoint bits, so
+// a pass computes ONE swizzle per lane; all other addresses are XORs with constants.
 //
-// Twiddles: exp(-2 pi i q / 1024) for q < 512 in shared memory; the second half
-// of the circle is the negated first half.
+// Twiddles: exp(-2 pi i q / 1024) for q < 512 in shared memory, behind a swizzle of their own
+// (fft_twi); the second half of the circle is the negated first half.
+//
+// tests/host/fft_check.cu replays the passes thread by thread on the host (bit equality of both
+// forms, a long-double DFT, the wavefront count of every access).
 //
 // Replaces the reference's calls into GstFFTF64/kissfft
 // (/root/reference/src/fftearmodel.c:457, movs.c:1301-1313,1428).

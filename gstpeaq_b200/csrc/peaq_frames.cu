@@ -1,8 +1,8 @@
 // K1 `fft_frames`: the stateless, frame-parallel half of the PEAQ hot path as a kernel of its own
-// -- one CTA per (pair, frame), results to per-frame records in HBM for the scan kernels.  Used
-// where the batch does not fill the GPU with one CTA per pair (few long items, sessions, the
-// advanced mode's FFT clock); large basic-mode batches run the fused persistent kernel
-// (peaq_fused.cu) instead.  The device code is frame_body in peaq_frames.cuh.
+// -- one CTA per (pair, frame), results to per-frame records in HBM for the scan kernels.  This is
+// the default path in both modes (basic: followed by K2 scan_basic_kernel; advanced: the FFT clock
+// next to the filter bank); the fused persistent kernel (peaq_fused.cu, PEAQ_B200_FUSED=1) runs the
+// same device code, frame_body in peaq_frames.cuh, inside a loop over a pair's frames.
 #include "peaq_frames.cuh"
 
 namespace peaq {

@@ -489,6 +489,43 @@ print(json.dumps({"movs": out["movs"][0][:5].tolist(), "odg": float(out["odg"][0
     assert abs(a["odg"] - b["odg"]) < 1e-9
 
 
+def test_filter_bank_coefficient_sources_same_bits():
+    """fb_bank_rec_kernel reads the entering side's coefficients from constant memory (uniform
+    datapath) by default and from shared memory with PEAQ_B200_FB_SMEM_COEF=1 (read once per
+    process, hence the subprocess): same products in the same order, so the per-frame excitations
+    and the results must be the same bits -- also for a second engine of the process (the constant
+    table is uploaded once per device)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import json, sys, hashlib, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import gstpeaq_b200 as G
+from signals import synth_pair
+ch = 2
+ref, test = synth_pair(91, 40000, ch)
+digest = []
+for level in (92.0, 80.0):
+    e = G.Engine(0, advanced=True, playback_level=level)
+    e.keep_records(True)
+    out = e.run_host(ref, test, ch)
+    exc, movs = e.fb_debug(1, ch)
+    digest.append(hashlib.sha256(np.asarray(exc[0]).tobytes() + out.tobytes()).hexdigest())
+    e.close()
+print(json.dumps(digest))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for smem in ("0", "1"):
+        env = dict(os.environ, PEAQ_B200_FB_SMEM_COEF=smem)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[smem] = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["0"] == res["1"]
+    assert res["0"][0] != res["0"][1]   # the two playback levels do differ
+
+
 @pytest.mark.parametrize("advanced", [False, True])
 def test_unaligned_mono_batch_matches_oracle(advanced):
     """mono pairs at an odd stride: every pair but the first starts off the 16-byte grid, so the
