@@ -1,7 +1,8 @@
 """SASS evidence per kernel of libpeaq_b200.so (runs on the CPU: cuobjdump of the built objects):
 instruction mix -- FP64 (DFMA/DMUL/DADD), shared memory, shuffles, TMA bulk copies (UBLKCP) and
-mbarrier operations (SYNCS), named barriers, tensor-core instructions (none expected on this path)
--- static counts per kernel.  usage: python scripts/sass_summary.py > profiles/<tag>_sass_summary.txt"""
+mbarrier operations (SYNCS), named barriers, constant-memory loads on the uniform datapath (LDCU
+from bank 3, the user's __constant__ data) and DFMAs that take a uniform-register operand,
+tensor-core instructions (none expected on this path) -- static counts per kernel.  usage: python scripts/sass_summary.py > profiles/<tag>_sass_summary.txt"""
 import collections, glob, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASSES = [("DFMA", r"^DFMA"), ("DMUL", r"^DMUL"), ("DADD", r"^DADD"), ("MUFU.64H", r"^MUFU\.(RCP|RSQ)64H"),
@@ -28,13 +29,20 @@ def main():
                 for name, pat in CLASSES:
                     if re.match(pat, op):
                         counts[kernel][name] += 1
+                if op.startswith("LDCU") and "c[0x3]" in ln:
+                    counts[kernel]["LDCU c[0x3] (uniform datapath)"] += 1
+                if op.startswith("DFMA") and re.search(r"\bUR\d+", ln):
+                    counts[kernel]["DFMA with UR operand"] += 1
         for kernel, c in counts.items():
             if c["total"] < 40:
                 continue
             dem = subprocess.run(["cu++filt", kernel], capture_output=True, text=True).stdout.strip() or kernel
-            short = re.sub(r"\(.*", "", dem).split("::")[-1]
+            # "void peaq::<unnamed>::name<(bool)1>(params)" -> "name<1>"
+            m = re.search(r"::([A-Za-z_]\w*)(<[^>]*>)?\(", dem)
+            short = (m.group(1) + re.sub(r"\((?:bool|int)\)", "", m.group(2) or "")) if m else dem
             print("%s  [%s]  %d instructions (%.0f KB)" % (short, os.path.basename(obj), c["total"], c["total"] * 16 / 1024.))
-            print("    " + "  ".join("%s %d" % (n, c[n]) for n, _ in CLASSES if c[n]))
+            names = [n for n, _ in CLASSES] + ["LDCU c[0x3] (uniform datapath)", "DFMA with UR operand"]
+            print("    " + "  ".join("%s %d" % (n, c[n]) for n in names if c[n]))
 
 if __name__ == "__main__":
     main()
