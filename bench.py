@@ -523,6 +523,10 @@ def measure(c, mode, pairs_gpu, seconds, steps, warmup, cpu_pairs, e2e_steps, wh
         roofline["ncu_capture"] = facts.get("capture")
         roofline["fp64_pipe_active_pct_ncu"] = facts.get("fp64_pipe_active_pct")
         roofline["issue_active_pct_ncu"] = facts.get("issue_active_pct")
+        # the SM's shared-memory / L1 data pipe (one 128-byte wavefront per cycle): the third resource
+        # these kernels lean on
+        roofline["lsu_data_pipe_pct_ncu"] = facts.get("lsu_data_pipe_pct")
+        roofline["shared_wavefronts_per_frame_ncu"] = facts.get("shared_wavefronts_per_frame")
     else:
         roofline["traffic"] = None
         roofline["traffic_note"] = why

@@ -52,6 +52,7 @@ def facts(raw, frames, capture):
         "warps_active_pct": raw.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
         "warp_inst_per_frame": raw.get("smsp__inst_executed.sum", 0.0) / frames,
         "registers_per_thread": raw.get("launch__registers_per_thread"),
+        "lsu_data_pipe_pct": raw.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
         "shared_wavefronts_per_frame": raw.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", 0.0) / frames,
         "shared_bank_conflicts_per_frame": raw.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 0.0) / frames,
     }
