@@ -11,7 +11,12 @@ CLASSES = [("DFMA", r"^DFMA"), ("DMUL", r"^DMUL"), ("DADD", r"^DADD"), ("MUFU.64
            ("LDGSTS (cp.async)", r"^LDGSTS"), ("BAR", r"^BAR"), ("CALL", r"^CALL"),
            ("tensor (HMMA/DMMA/UTC*MMA)", r"^(HMMA|DMMA|IMMA|UTC[A-Z]*MMA|TCGEN)")]
 
-def main():
+EXTRA = ["LDCU c[0x3] (uniform datapath)", "DFMA with UR operand"]
+
+
+def collect():
+    """{kernel name: {"object": file, "total": n, class: count, ...}} over the built kernel objects"""
+    res = collections.OrderedDict()
     for obj in sorted(glob.glob(os.path.join(ROOT, "gstpeaq_b200", "csrc", "build", "*.o"))):
         out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
         kernel = None
@@ -30,9 +35,9 @@ def main():
                     if re.match(pat, op):
                         counts[kernel][name] += 1
                 if op.startswith("LDCU") and "c[0x3]" in ln:
-                    counts[kernel]["LDCU c[0x3] (uniform datapath)"] += 1
+                    counts[kernel][EXTRA[0]] += 1
                 if op.startswith("DFMA") and re.search(r"\bUR\d+", ln):
-                    counts[kernel]["DFMA with UR operand"] += 1
+                    counts[kernel][EXTRA[1]] += 1
         for kernel, c in counts.items():
             if c["total"] < 40:
                 continue
@@ -40,9 +45,16 @@ def main():
             # "void peaq::<unnamed>::name<(bool)1>(params)" -> "name<1>"
             m = re.search(r"::([A-Za-z_]\w*)(<[^>]*>)?\(", dem)
             short = (m.group(1) + re.sub(r"\((?:bool|int)\)", "", m.group(2) or "")) if m else dem
-            print("%s  [%s]  %d instructions (%.0f KB)" % (short, os.path.basename(obj), c["total"], c["total"] * 16 / 1024.))
-            names = [n for n, _ in CLASSES] + ["LDCU c[0x3] (uniform datapath)", "DFMA with UR operand"]
-            print("    " + "  ".join("%s %d" % (n, c[n]) for n in names if c[n]))
+            res[short] = dict(c, object=os.path.basename(obj))
+    return res
+
+
+def main():
+    for short, c in collect().items():
+        print("%s  [%s]  %d instructions (%.0f KB)" % (short, c["object"], c["total"], c["total"] * 16 / 1024.))
+        names = [n for n, _ in CLASSES] + EXTRA
+        print("    " + "  ".join("%s %d" % (n, c[n]) for n in names if c.get(n)))
+
 
 if __name__ == "__main__":
     main()

@@ -267,3 +267,29 @@ def test_frame_kernel_fft_two_trip_form_replayed_on_the_host(tmp_path):
                            os.path.join(ROOT, "tests", "host", "fft_check.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
+def test_sass_of_the_built_kernels_has_what_design_md_claims():
+    """static SASS facts of the in-tree build (scripts/sass_summary.py over the kernel objects): the
+    frame kernel stages PCM with TMA bulk copies behind an mbarrier, the filter bank reads half of
+    its coefficients from constant memory on the uniform datapath (LDCU from bank 3, DFMAs with a
+    uniform-register operand), its shared-memory cross-check form does not, and nothing on the path
+    uses tensor cores"""
+    import glob
+    import shutil
+    import subprocess
+    import sys
+    if not shutil.which("cuobjdump") or not glob.glob(os.path.join(ROOT, "gstpeaq_b200", "csrc", "build", "*.o")):
+        pytest.skip("no cuobjdump or no kernel objects (library not built in this tree)")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import sass_summary
+    facts = sass_summary.collect()
+    k1 = facts["fft_frames_kernel"]
+    assert k1.get("UBLKCP (TMA bulk)", 0) >= 2 and k1.get("SYNCS (mbarrier)", 0) >= 1, k1
+    assert k1.get("DFMA", 0) > 300 and k1.get("LDS", 0) > 100
+    fb_const, fb_smem = facts["fb_bank_rec_kernel<1>"], facts["fb_bank_rec_kernel<0>"]
+    assert fb_const.get("LDCU c[0x3] (uniform datapath)", 0) >= 48 and fb_const.get("DFMA with UR operand", 0) >= 400, fb_const
+    assert fb_smem.get("LDCU c[0x3] (uniform datapath)", 0) == 0
+    assert fb_const.get("LDGSTS (cp.async)", 0) >= 1
+    for name, f in facts.items():
+        assert not any(k.startswith("tensor") and v for k, v in f.items()), (name, f)
